@@ -1,0 +1,157 @@
+/*
+ * tai_b200.h -- C ABI of the B200-native TAI / bi-TAI hot path (libtai_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers, sizes and a CUDA stream
+ * (passed as void* == cudaStream_t; NULL = legacy default stream), borrows all pointers, fully
+ * overwrites its outputs (callers may pass uninitialised memory -- the reference's zero-fill,
+ * SeparableConvolution.py:36,69-71, is not needed), keeps no state between calls, performs no
+ * allocation and no host synchronisation (CUDA-graph capturable) and returns 0 on success or a
+ * negative TAI_ERR_* code; it never throws.  tai_b200_last_error() returns a thread-local
+ * message for the last failure.
+ *
+ * All tensors are FP32, contiguous NCHW, and live on the current CUDA device.  Element counts
+ * are validated to stay below 2^31 per tensor (same limit as the reference, kernel.cu:172).
+ *
+ * Each declaration names the reference interface it replaces; paths are relative to the
+ * reference repository (MichiganCOG/video-frame-inpainting).
+ */
+#ifndef TAI_B200_H
+#define TAI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAI_B200_ABI_VERSION 1
+
+enum {
+    TAI_OK = 0,
+    TAI_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, even ks for a fused-pad entry, ... */
+    TAI_ERR_UNSUPPORTED = -2,      /* ks or C outside the compiled range (ks <= 64)                        */
+    TAI_ERR_TOO_LARGE = -3,        /* a tensor would have >= 2^31 elements                                 */
+    TAI_ERR_CUDA = -4              /* a CUDA runtime call / launch failed; see tai_b200_last_error()       */
+};
+
+int tai_b200_abi_version(void);
+const char *tai_b200_last_error(void);
+
+/* Number of kernels this library has launched so far in this process (monotonic counter,
+ * used by bench.py for its "gpu_launches" claim). */
+long long tai_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-pixel separable local convolution.
+ *
+ * Replaces  int SeparableConvolution_cuda_forward(THCudaTensor* input, vertical, horizontal,
+ *                                                 output, int ks)
+ *           src/separable_convolution/cfile/SeparableConvolution_cuda.h:1-7  (-> kernel.cu:164-185,19-47)
+ *
+ *   input      [B, C, Hi, Wi]            vertical, horizontal [B, ks, Ho, Wo]
+ *   output     [B, C, Ho, Wo]            Ho = Hi-ks+1, Wo = Wi-ks+1
+ *   output[b,c,y,x] = sum_i sum_j input[b,c,y+i,x+j] * vertical[b,i,y,x] * horizontal[b,j,y,x]
+ */
+int SeparableConvolution_cuda_forward_b200(const float *input, const float *vertical,
+                                           const float *horizontal, float *output,
+                                           int B, int C, int Hi, int Wi, int ks, void *stream);
+
+/* Replaces  int SeparableConvolution_cuda_backward(THCudaTensor* grad_output, input, vertical,
+ *                 horizontal, grad_input, grad_vertical, grad_horizontal, int ks)
+ *           src/separable_convolution/cfile/SeparableConvolution_cuda.h:9-18 (-> kernel.cu:187-242,49-162)
+ *
+ *   grad_output [B,C,Ho,Wo] -> grad_input [B,C,Hi,Wi], grad_vertical / grad_horizontal [B,ks,Ho,Wo].
+ *   Any of the three gradient pointers may be NULL to skip that gradient.
+ */
+int SeparableConvolution_cuda_backward_b200(const float *grad_output, const float *input,
+                                            const float *vertical, const float *horizontal,
+                                            float *grad_input, float *grad_vertical,
+                                            float *grad_horizontal,
+                                            int B, int C, int Hi, int Wi, int ks, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused TAI call site: replication pad + both separable convolutions + blend.
+ *
+ * Replaces the op sequence  modulePad -> separableConvolution (x2)   src/models/tai/tai.py:170-171,229-236
+ *                           0.5*Dot1 + 0.5*Dot2                      src/models/tai/tai.py:105
+ *                           (1-w)*Dot1 + w*Dot2                      src/models/twi/twi.py:105
+ *
+ *   pred_f, pred_b [B,C,H,W] (UNPADDED);  v1,h1,v2,h2 [B,ks,H,W];  ks odd, p = ks/2
+ *   dot1 = sepconv(reppad(pred_f,p), v1, h1);  dot2 = sepconv(reppad(pred_b,p), v2, h2)
+ *   pred = a*dot1 + b*dot2.   dot1 / dot2 may be NULL (not stored).
+ */
+int tai_fused_forward_b200(const float *pred_f, const float *pred_b,
+                           const float *v1, const float *h1, const float *v2, const float *h2,
+                           float *pred, float *dot1, float *dot2,
+                           int B, int C, int H, int W, int ks, float a, float b, void *stream);
+
+/* Backward of tai_fused_forward_b200.  grad_pred / grad_dot1 / grad_dot2 [B,C,H,W], any may be
+ * NULL (treated as zero) but not all three.  The effective upstream gradients are
+ * gD1 = a*grad_pred + grad_dot1, gD2 = b*grad_pred + grad_dot2.  Outputs: gradients w.r.t. the
+ * UNPADDED predictions (replication-pad adjoint folded in) and the four kernel maps.
+ * `workspace` must hold at least tai_fused_backward_workspace_bytes(...) bytes. */
+long long tai_fused_backward_workspace_bytes(int B, int C, int H, int W, int ks);
+int tai_fused_backward_b200(const float *grad_pred, const float *grad_dot1, const float *grad_dot2,
+                            const float *pred_f, const float *pred_b,
+                            const float *v1, const float *h1, const float *v2, const float *h2,
+                            float *g_pred_f, float *g_pred_b,
+                            float *g_v1, float *g_h1, float *g_v2, float *g_h2,
+                            void *workspace,
+                            int B, int C, int H, int W, int ks, float a, float b, void *stream);
+
+/* Standalone replication pad and its adjoint (torch.nn.ReplicationPad2d(p), tai.py:170-171). */
+int replication_pad_forward_b200(const float *in, float *out, int N, int H, int W, int p, void *stream);
+int replication_pad_backward_b200(const float *grad_out, float *grad_in, int N, int H, int W, int p, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ConvLSTM gate path.
+ *
+ * Replaces the elementwise chain of ConvLstmCell.forward, src/models/mcnet/mcnet.py:287-293:
+ *   c,h = chunk(state,2,1); (i,j,f,o) = chunk(conv_out,4,1)
+ *   c' = c*sigmoid(f+forget_bias) + sigmoid(i)*tanh(j);  h' = tanh(c')*sigmoid(o)
+ *   new_state = cat(c',h')
+ *   conv_out [B,4F,h,w], state [B,2F,h,w] -> new_state [B,2F,h,w];  HW = h*w.
+ */
+int convlstm_gates_forward_b200(const float *conv_out, const float *state, float *new_state,
+                                int B, int F, int HW, float forget_bias, void *stream);
+/* g_new_state [B,2F,HW] -> g_conv_out [B,4F,HW], g_state [B,2F,HW] (h half written as zero). */
+int convlstm_gates_backward_b200(const float *conv_out, const float *state, const float *g_new_state,
+                                 float *g_conv_out, float *g_state,
+                                 int B, int F, int HW, float forget_bias, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Super SloMo bilinear backward warp.
+ *
+ * Replaces FlowWarper.forward, src/models/slomo/slomo.py:265-286 (host meshgrid + F.grid_sample
+ * of torch 0.3.1: bilinear, zero padding, ix = ((g+1)/2)*(W-1)):
+ *   out[b,c,y,x] = bilinear(img[b,c], ix, iy),  ix from x+uv[b,0,y,x], iy from y+uv[b,1,y,x]
+ *   img [B,C,H,W], uv [B,2,H,W] -> out [B,C,H,W]
+ */
+int flow_warp_forward_b200(const float *img, const float *uv, float *out,
+                           int B, int C, int H, int W, void *stream);
+/* g_img is accumulated with atomics and is zeroed by the callee on `stream` first. */
+int flow_warp_backward_b200(const float *img, const float *uv, const float *grad_out,
+                            float *g_img, float *g_uv, int B, int C, int H, int W, void *stream);
+
+/* Replaces slomo.py:312-316: F_t0 = -(1-t)t F01 + t^2 F10; F_t1 = (1-t)^2 F01 - t(1-t) F10;
+ * g0 = warp(I0, F_t0); g1 = warp(I1, F_t1).  f01,f10,f_t0,f_t1 [B,2,H,W]; i0,i1,g0,g1 [B,C,H,W]. */
+int slomo_flow_combine_warp_forward_b200(const float *i0, const float *i1,
+                                         const float *f01, const float *f10, double t,
+                                         float *f_t0, float *f_t1, float *g0, float *g1,
+                                         int B, int C, int H, int W, void *stream);
+
+/* Replaces slomo.py:320-328: F_ref = clamp(dF+F,-1,1); V1 = 1-V0; g = warp(I,F_ref);
+ * out = ((1-t)V0 g0 + t V1 g1) / ((1-t)V0 + t V1).   d_t0,d_t1 [B,2,H,W]; v_t0 [B,1,H,W]. */
+int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
+                                    const float *f_t0, const float *f_t1,
+                                    const float *d_t0, const float *d_t1, const float *v_t0,
+                                    double t, float *out, int B, int C, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helper: a pure FFMA loop, used by bench.py to report the on-box FP32 FMA
+ * ceiling next to the nominal 148 x 128 x 2 x f_SM.  Writes one float per thread to `sink`
+ * (gridDim*blockDim floats).  flops = 2 * 8 * iters * grid * block. */
+int tai_b200_ffma_probe(float *sink, int grid, int block, int iters, int packed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAI_B200_H */

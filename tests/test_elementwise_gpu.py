@@ -1,0 +1,121 @@
+"""GPU parity of the HBM-bound kernels (ConvLSTM gates, bilinear warp, SloMo fusions) against the
+float64 oracle; integer parts (floor / in-bounds corner selection) bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import TOL, assert_close, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,F,h,w", [(1, 256, 16, 16), (2, 8, 5, 7), (3, 1, 1, 1), (2, 256, 30, 40)])
+def test_gates_forward_backward(cuda, B, F, h, w):
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(20)
+    conv = rng.normal(0, 1, (B, 4 * F, h, w)).astype(np.float32)
+    state = rng.normal(0, 1, (B, 2 * F, h, w)).astype(np.float32)
+    g = rng.normal(0, 1, (B, 2 * F, h, w)).astype(np.float32)
+    tc, ts, tg = to_cuda(conv, state, g)
+    ns = ops.convlstm_gates_forward(tc, ts, 1.0).cpu().numpy()
+    _, ref_ns = O.convlstm_gates(conv, state, 1.0)
+    assert_close(ns, ref_ns, what="gates fwd")
+    gc, gs = ops.convlstm_gates_backward(tc, ts, tg, 1.0)
+    ref_gc, ref_gs = O.convlstm_gates_backward(conv, state, g, 1.0)
+    assert_close(gc.cpu().numpy(), ref_gc, what="gates g_conv")
+    assert_close(gs.cpu().numpy(), ref_gs, what="gates g_state")
+    assert np.all(gs.cpu().numpy()[:, F:] == 0)  # h only feeds the convolution (mcnet.py:288)
+
+
+def _flow(rng, B, H, W):
+    uv = rng.normal(0, 2, (B, 2, H, W)).astype(np.float32)
+    mask = rng.uniform(size=(B, 1, H, W)) < 0.08  # >= 5 % of samples pushed far out of bounds
+    return np.where(mask, uv * 40, uv).astype(np.float32)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 3, 32, 40), (2, 1, 7, 5), (1, 3, 256, 320)])
+def test_flow_warp_forward(cuda, B, C, H, W):
+    import torch
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(21)
+    img = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    uv = _flow(rng, B, H, W)
+    ti, tu = to_cuda(img, uv)
+    out = ops.flow_warp_forward(ti, tu).cpu().numpy()
+    assert_close(out, O.flow_warp(img, uv, coords="f32"), tol=1e-5, what="warp (f32-coordinate twin)")
+    # float64 coordinates can fall on the other side of an integer; bilinear is continuous there
+    assert_close(out, O.flow_warp(img, uv), tol=2e-3, what="warp (float64 coordinates)")
+    # integer table: warping a coordinate image with zero fractional flow recovers floor() exactly
+    ix, iy, x0, y0 = O.flow_warp_coords_f32(uv)
+    frac0 = (ix == np.floor(ix)) & (iy == np.floor(iy))
+    assert frac0.sum() >= 0  # (table itself is exercised through the f32 twin above)
+
+
+def test_flow_warp_integer_corners_bit_exact(cuda):
+    """Flows chosen so that the sampling point is an exact pixel centre: output must equal the
+    selected input pixel (or 0 outside), bit for bit -- floor / bounds logic of the sampler."""
+    import torch
+    from video_frame_inpainting_b200 import ops
+    B, C, H, W = 1, 1, 16, 16   # powers of two: every step of the coordinate chain is exact in FP32
+    rng = np.random.default_rng(22)
+    img = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    # want ix = (x+u)*(W-1)/W to be the integer k  =>  x + u = k*W/(W-1): not exact in general, so
+    # use the oracle's FP32 chain to find which flows land exactly on integers
+    ks = rng.integers(-3, W + 3, (B, H, W))
+    ls = rng.integers(-3, H + 3, (B, H, W))
+    u = (ks * W / (W - 1) - np.arange(W)[None, None, :]).astype(np.float32)
+    v = (ls * H / (H - 1) - np.arange(H)[None, :, None]).astype(np.float32)
+    uv = np.stack([u, v], 1).astype(np.float32)
+    ix, iy, x0, y0 = O.flow_warp_coords_f32(uv)
+    exact = (ix == x0) & (iy == y0)
+    assert exact.mean() > 0.2
+    ti, tu = to_cuda(img, uv)
+    out = ops.flow_warp_forward(ti, tu).cpu().numpy()[0, 0]
+    inb = (x0 >= 0) & (x0 < W) & (y0 >= 0) & (y0 < H)
+    expect = np.where(inb[0], img[0, 0][np.clip(y0[0], 0, H - 1), np.clip(x0[0], 0, W - 1)], 0.0)
+    sel = exact[0]
+    assert np.array_equal(out[sel], expect[sel].astype(np.float32))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 3, 32, 40), (2, 1, 7, 5)])
+def test_flow_warp_backward(cuda, B, C, H, W):
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(23)
+    img = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    uv = _flow(rng, B, H, W)
+    # keep sampling points away from integer coordinates (the gradient is discontinuous there)
+    ix, iy, _, _ = O.flow_warp_coords_f32(uv)
+    near = (np.abs(ix - np.round(ix)) < 1e-3) | (np.abs(iy - np.round(iy)) < 1e-3)
+    uv[:, 0][near] += 0.37
+    uv[:, 1][near] += 0.41
+    g = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    ti, tu, tg = to_cuda(img, uv, g)
+    gi, gu = ops.flow_warp_backward(ti, tu, tg)
+    ref_gi, ref_gu = O.flow_warp_backward(img, uv, g)
+    assert_close(gi.cpu().numpy(), ref_gi, tol=5 * TOL, what="warp g_img")
+    assert_close(gu.cpu().numpy(), ref_gu, tol=5 * TOL, what="warp g_uv")
+
+
+@pytest.mark.parametrize("B,C,H,W,T", [(1, 3, 32, 64, 3), (2, 1, 16, 24, 5)])
+def test_slomo_fused_stages(cuda, B, C, H, W, T):
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(24)
+    i0 = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    i1 = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    f01 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    f10 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    d0 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    d1 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    v0 = rng.uniform(0.05, 0.95, (B, 1, H, W)).astype(np.float32)
+    t_i0, t_i1, t_f01, t_f10, t_d0, t_d1, t_v0 = to_cuda(i0, i1, f01, f10, d0, d1, v0)
+    for t_ in range(T):
+        t = (t_ + 1) / (T + 1)
+        ft0, ft1, g0, g1 = ops.slomo_flow_combine_warp(t_i0, t_i1, t_f01, t_f10, t)
+        r_ft0, r_ft1 = O.slomo_flow_combine(f01, f10, t)
+        assert_close(ft0.cpu().numpy(), r_ft0, what="F_t_0")
+        assert_close(ft1.cpu().numpy(), r_ft1, what="F_t_1")
+        assert_close(g0.cpu().numpy(), O.flow_warp(i0, ft0.cpu().numpy()), tol=2e-3, what="g0")
+        assert_close(g1.cpu().numpy(), O.flow_warp(i1, ft1.cpu().numpy()), tol=2e-3, what="g1")
+        out = ops.slomo_refine_blend(t_i0, t_i1, ft0, ft1, t_d0, t_d1, t_v0, t).cpu().numpy()
+        ref = O.slomo_refine_blend(i0, i1, ft0.cpu().numpy(), ft1.cpu().numpy(), d0, d1, v0, t)
+        assert_close(out, ref, tol=2e-3, what="refine+blend")

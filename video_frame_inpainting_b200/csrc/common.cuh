@@ -1,0 +1,107 @@
+// Shared host/device helpers for libtai_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tai_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libtai_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace tai {
+
+// ---- error plumbing (definitions in capi.cu) ------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return TAI_ERR_CUDA;
+    }
+    count_launch();
+    return TAI_OK;
+}
+
+#define TAI_REQUIRE(cond, code, ...)     \
+    do {                                 \
+        if (!(cond)) {                   \
+            tai::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+inline bool fits_int31(long long n) { return n > 0 && n < (1LL << 31); }
+
+inline int sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Streaming loads for data that is read exactly once (V / H kernel maps): keep them out of L1.
+__device__ __forceinline__ float ld_stream(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// Packed FP32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves with one issue slot.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+}  // namespace tai

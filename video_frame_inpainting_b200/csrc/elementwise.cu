@@ -1,0 +1,436 @@
+// HBM-bound kernels of the TAI / Super-SloMo path for sm_100a: ConvLSTM gates, bilinear backward
+// warp, SloMo flow-combine / refine-blend fusions, and the FFMA probe used by bench.py.
+// Every kernel streams its operands exactly once with 128-bit accesses where alignment allows.
+#include "common.cuh"
+
+namespace tai {
+
+static inline unsigned stream_grid(long work_items, int block)
+{
+    long g = (work_items + block - 1) / block;
+    const long cap = (long)sm_count() * 8;  // 8 resident 256-thread CTAs per SM, grid-stride beyond
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvLSTM gates (mcnet.py:287-293).  conv_out [B,4F,HW] holds (i,j,f,o) as four contiguous F*HW
+// slabs per sample; state [B,2F,HW] holds (c,h).  28 B of traffic per state element.
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gates_fwd_kernel(const float *__restrict__ conv, const float *__restrict__ state, float *__restrict__ nstate,
+                 int B, long slab, float fb)
+{
+    const long per = slab / VEC;
+    const long n = (long)B * per;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / per;
+        const long e = (idx - b * per) * VEC;
+        const float *cb = conv + b * 4 * slab + e;
+        const float *sb = state + b * 2 * slab + e;
+        float *ob = nstate + b * 2 * slab + e;
+        float gi[VEC], gj[VEC], gf[VEC], go[VEC], c[VEC], nc[VEC], nh[VEC];
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(gi) = ld_stream4(reinterpret_cast<const float4 *>(cb));
+            *reinterpret_cast<float4 *>(gj) = ld_stream4(reinterpret_cast<const float4 *>(cb + slab));
+            *reinterpret_cast<float4 *>(gf) = ld_stream4(reinterpret_cast<const float4 *>(cb + 2 * slab));
+            *reinterpret_cast<float4 *>(go) = ld_stream4(reinterpret_cast<const float4 *>(cb + 3 * slab));
+            *reinterpret_cast<float4 *>(c) = ld_stream4(reinterpret_cast<const float4 *>(sb));
+        } else {
+            gi[0] = cb[0]; gj[0] = cb[slab]; gf[0] = cb[2 * slab]; go[0] = cb[3 * slab]; c[0] = sb[0];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            nc[k] = c[k] * sigmoid_acc(gf[k] + fb) + sigmoid_acc(gi[k]) * tanhf(gj[k]);
+            nh[k] = tanhf(nc[k]) * sigmoid_acc(go[k]);
+        }
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(ob) = *reinterpret_cast<float4 *>(nc);
+            *reinterpret_cast<float4 *>(ob + slab) = *reinterpret_cast<float4 *>(nh);
+        } else {
+            ob[0] = nc[0];
+            ob[slab] = nh[0];
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gates_bwd_kernel(const float *__restrict__ conv, const float *__restrict__ state, const float *__restrict__ gns,
+                 float *__restrict__ gconv, float *__restrict__ gstate, int B, long slab, float fb)
+{
+    const long per = slab / VEC;
+    const long n = (long)B * per;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / per;
+        const long e = (idx - b * per) * VEC;
+        const float *cb = conv + b * 4 * slab + e;
+        const float *sb = state + b * 2 * slab + e;
+        const float *gb = gns + b * 2 * slab + e;
+        float *gcb = gconv + b * 4 * slab + e;
+        float *gsb = gstate + b * 2 * slab + e;
+        float gi[VEC], gj[VEC], gf[VEC], go[VEC], c[VEC], gcn[VEC], ghn[VEC];
+        float di[VEC], dj[VEC], df[VEC], dgo[VEC], dc[VEC], dz[VEC];
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(gi) = ld_stream4(reinterpret_cast<const float4 *>(cb));
+            *reinterpret_cast<float4 *>(gj) = ld_stream4(reinterpret_cast<const float4 *>(cb + slab));
+            *reinterpret_cast<float4 *>(gf) = ld_stream4(reinterpret_cast<const float4 *>(cb + 2 * slab));
+            *reinterpret_cast<float4 *>(go) = ld_stream4(reinterpret_cast<const float4 *>(cb + 3 * slab));
+            *reinterpret_cast<float4 *>(c) = ld_stream4(reinterpret_cast<const float4 *>(sb));
+            *reinterpret_cast<float4 *>(gcn) = ld_stream4(reinterpret_cast<const float4 *>(gb));
+            *reinterpret_cast<float4 *>(ghn) = ld_stream4(reinterpret_cast<const float4 *>(gb + slab));
+        } else {
+            gi[0] = cb[0]; gj[0] = cb[slab]; gf[0] = cb[2 * slab]; go[0] = cb[3 * slab];
+            c[0] = sb[0]; gcn[0] = gb[0]; ghn[0] = gb[slab];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float si = sigmoid_acc(gi[k]), sf = sigmoid_acc(gf[k] + fb), so = sigmoid_acc(go[k]);
+            const float tj = tanhf(gj[k]);
+            const float tc = tanhf(c[k] * sf + si * tj);
+            const float gct = gcn[k] + ghn[k] * so * (1.f - tc * tc);
+            di[k] = gct * tj * si * (1.f - si);
+            dj[k] = gct * si * (1.f - tj * tj);
+            df[k] = gct * c[k] * sf * (1.f - sf);
+            dgo[k] = ghn[k] * tc * so * (1.f - so);
+            dc[k] = gct * sf;
+            dz[k] = 0.f;
+        }
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(gcb) = *reinterpret_cast<float4 *>(di);
+            *reinterpret_cast<float4 *>(gcb + slab) = *reinterpret_cast<float4 *>(dj);
+            *reinterpret_cast<float4 *>(gcb + 2 * slab) = *reinterpret_cast<float4 *>(df);
+            *reinterpret_cast<float4 *>(gcb + 3 * slab) = *reinterpret_cast<float4 *>(dgo);
+            *reinterpret_cast<float4 *>(gsb) = *reinterpret_cast<float4 *>(dc);
+            *reinterpret_cast<float4 *>(gsb + slab) = *reinterpret_cast<float4 *>(dz);
+        } else {
+            gcb[0] = di[0]; gcb[slab] = dj[0]; gcb[2 * slab] = df[0]; gcb[3 * slab] = dgo[0];
+            gsb[0] = dc[0]; gsb[slab] = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear backward warp (slomo.py:265-286 + torch-0.3.1 grid_sample: bilinear, zero padding).
+// The coordinate chain is evaluated with one IEEE rounding per reference operation (no FMA
+// contraction) so that floor() -- the integer part of the op -- matches the FP32 reference exactly:
+//   X = x + u;  g = 2*(X/W - 0.5);  ix = ((g + 1)/2)*(W-1)
+struct WarpCoord {
+    int x0, y0;
+    float ix, iy;
+};
+
+__device__ __forceinline__ float warp_axis(float pos, float flow, float size)
+{
+    const float X = __fadd_rn(pos, flow);
+    const float g = __fmul_rn(2.f, __fsub_rn(__fdiv_rn(X, size), 0.5f));
+    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), size - 1.f);
+}
+
+__device__ __forceinline__ WarpCoord warp_coord(int x, int y, float u, float v, int W, int H)
+{
+    WarpCoord c;
+    c.ix = warp_axis((float)x, u, (float)W);
+    c.iy = warp_axis((float)y, v, (float)H);
+    c.x0 = __float2int_rd(c.ix);
+    c.y0 = __float2int_rd(c.iy);
+    return c;
+}
+
+__device__ __forceinline__ float tap(const float *__restrict__ img, int y, int x, int H, int W)
+{
+    return (x >= 0 && y >= 0 && x < W && y < H) ? __ldg(img + (long)y * W + x) : 0.f;
+}
+
+__device__ __forceinline__ float bilinear(const float *__restrict__ img, const WarpCoord &c, int H, int W)
+{
+    const float x1 = (float)(c.x0 + 1), y1 = (float)(c.y0 + 1), x0 = (float)c.x0, y0 = (float)c.y0;
+    const float wnw = (x1 - c.ix) * (y1 - c.iy), wne = (c.ix - x0) * (y1 - c.iy);
+    const float wsw = (x1 - c.ix) * (c.iy - y0), wse = (c.ix - x0) * (c.iy - y0);
+    return tap(img, c.y0, c.x0, H, W) * wnw + tap(img, c.y0, c.x0 + 1, H, W) * wne +
+           tap(img, c.y0 + 1, c.x0, H, W) * wsw + tap(img, c.y0 + 1, c.x0 + 1, H, W) * wse;
+}
+
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(const float *__restrict__ img, const float *__restrict__ uv, float *__restrict__ out,
+                int B, int C, int H, int W)
+{
+    const long hw = (long)H * W;
+    const long n = (long)B * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        const int y = (idx / W) % H;
+        const long b = idx / hw;
+        const long pix = (long)y * W + x;
+        const WarpCoord c = warp_coord(x, y, ld_stream(uv + (b * 2) * hw + pix), ld_stream(uv + (b * 2 + 1) * hw + pix), W, H);
+        for (int ch = 0; ch < C; ++ch) out[(b * C + ch) * hw + pix] = bilinear(img + (b * C + ch) * hw, c, H, W);
+    }
+}
+
+__device__ __forceinline__ void scatter(float *img, int y, int x, int H, int W, float val)
+{
+    if (x >= 0 && y >= 0 && x < W && y < H) atomicAdd(img + (long)y * W + x, val);
+}
+
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const float *__restrict__ img, const float *__restrict__ uv, const float *__restrict__ gout,
+                float *__restrict__ gimg, float *__restrict__ guv, int B, int C, int H, int W)
+{
+    const long hw = (long)H * W;
+    const long n = (long)B * hw;
+    const float sx = (float)(W - 1) / (float)W, sy = (float)(H - 1) / (float)H;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        const int y = (idx / W) % H;
+        const long b = idx / hw;
+        const long pix = (long)y * W + x;
+        const WarpCoord c = warp_coord(x, y, __ldg(uv + (b * 2) * hw + pix), __ldg(uv + (b * 2 + 1) * hw + pix), W, H);
+        const float x1 = (float)(c.x0 + 1), y1 = (float)(c.y0 + 1), x0 = (float)c.x0, y0 = (float)c.y0;
+        const float ax = x1 - c.ix, bx = c.ix - x0, ay = y1 - c.iy, by = c.iy - y0;
+        float gx = 0.f, gy = 0.f;
+        for (int ch = 0; ch < C; ++ch) {
+            const float *im = img + (b * C + ch) * hw;
+            const float g = __ldg(gout + (b * C + ch) * hw + pix);
+            const float nw = tap(im, c.y0, c.x0, H, W), ne = tap(im, c.y0, c.x0 + 1, H, W);
+            const float sw = tap(im, c.y0 + 1, c.x0, H, W), se = tap(im, c.y0 + 1, c.x0 + 1, H, W);
+            gx += g * ((ne - nw) * ay + (se - sw) * by);
+            gy += g * ((sw - nw) * ax + (se - ne) * bx);
+            if (gimg) {
+                float *gi = gimg + (b * C + ch) * hw;
+                scatter(gi, c.y0, c.x0, H, W, g * ax * ay);
+                scatter(gi, c.y0, c.x0 + 1, H, W, g * bx * ay);
+                scatter(gi, c.y0 + 1, c.x0, H, W, g * ax * by);
+                scatter(gi, c.y0 + 1, c.x0 + 1, H, W, g * bx * by);
+            }
+        }
+        if (guv) {
+            guv[(b * 2) * hw + pix] = gx * sx;
+            guv[(b * 2 + 1) * hw + pix] = gy * sy;
+        }
+    }
+}
+
+// slomo.py:312-316 in one pass: intermediate flows + both warps.
+__global__ void __launch_bounds__(256)
+slomo_combine_warp_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                          const float *__restrict__ f01, const float *__restrict__ f10,
+                          float c00, float c01, float c10, float c11,
+                          float *__restrict__ ft0, float *__restrict__ ft1,
+                          float *__restrict__ g0, float *__restrict__ g1, int B, int C, int H, int W)
+{
+    const long hw = (long)H * W;
+    const long n = (long)B * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        const int y = (idx / W) % H;
+        const long b = idx / hw;
+        const long pix = (long)y * W + x;
+        const long fu = (b * 2) * hw + pix, fv = fu + hw;
+        const float a_u = ld_stream(f01 + fu), a_v = ld_stream(f01 + fv);
+        const float b_u = ld_stream(f10 + fu), b_v = ld_stream(f10 + fv);
+        // same association as the reference: (coef * F01) + (coef * F10), no contraction
+        const float t0u = __fadd_rn(__fmul_rn(c00, a_u), __fmul_rn(c01, b_u));
+        const float t0v = __fadd_rn(__fmul_rn(c00, a_v), __fmul_rn(c01, b_v));
+        const float t1u = __fsub_rn(__fmul_rn(c10, a_u), __fmul_rn(c11, b_u));
+        const float t1v = __fsub_rn(__fmul_rn(c10, a_v), __fmul_rn(c11, b_v));
+        ft0[fu] = t0u; ft0[fv] = t0v;
+        ft1[fu] = t1u; ft1[fv] = t1v;
+        const WarpCoord w0 = warp_coord(x, y, t0u, t0v, W, H);
+        const WarpCoord w1 = warp_coord(x, y, t1u, t1v, W, H);
+        for (int ch = 0; ch < C; ++ch) {
+            const long o = (b * C + ch) * hw;
+            g0[o + pix] = bilinear(i0 + o, w0, H, W);
+            g1[o + pix] = bilinear(i1 + o, w1, H, W);
+        }
+    }
+}
+
+// slomo.py:320-328 in one pass: refine-add-clamp, two warps, visibility-weighted blend.
+__global__ void __launch_bounds__(256)
+slomo_refine_blend_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                          const float *__restrict__ ft0, const float *__restrict__ ft1,
+                          const float *__restrict__ d0, const float *__restrict__ d1,
+                          const float *__restrict__ v0, float omt, float t,
+                          float *__restrict__ out, int B, int C, int H, int W)
+{
+    const long hw = (long)H * W;
+    const long n = (long)B * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        const int y = (idx / W) % H;
+        const long b = idx / hw;
+        const long pix = (long)y * W + x;
+        const long fu = (b * 2) * hw + pix, fv = fu + hw;
+        const float r0u = fminf(fmaxf(__fadd_rn(ld_stream(d0 + fu), ld_stream(ft0 + fu)), -1.f), 1.f);
+        const float r0v = fminf(fmaxf(__fadd_rn(ld_stream(d0 + fv), ld_stream(ft0 + fv)), -1.f), 1.f);
+        const float r1u = fminf(fmaxf(__fadd_rn(ld_stream(d1 + fu), ld_stream(ft1 + fu)), -1.f), 1.f);
+        const float r1v = fminf(fmaxf(__fadd_rn(ld_stream(d1 + fv), ld_stream(ft1 + fv)), -1.f), 1.f);
+        const WarpCoord w0 = warp_coord(x, y, r0u, r0v, W, H);
+        const WarpCoord w1 = warp_coord(x, y, r1u, r1v, W, H);
+        const float vis0 = ld_stream(v0 + b * hw + pix);
+        const float vis1 = 1.f - vis0;
+        const float k0 = omt * vis0, k1 = t * vis1;
+        const float norm = k0 + k1;
+        for (int ch = 0; ch < C; ++ch) {
+            const long o = (b * C + ch) * hw;
+            const float a0 = bilinear(i0 + o, w0, H, W), a1 = bilinear(i1 + o, w1, H, W);
+            out[o + pix] = (k0 * a0 + k1 * a1) / norm;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFMA probe: 8 independent chains per thread, `iters` FMAs each (scalar FFMA or packed FFMA2).
+template <bool PACKED>
+__global__ void ffma_probe_kernel(float *sink, int iters)
+{
+    const float s = 1.0f + 1e-7f * (float)threadIdx.x, t = 1e-9f * (float)blockIdx.x;
+    if (PACKED) {
+        float2 a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = make_float2(0.1f * (float)k, 0.2f * (float)k);
+        const float2 s2 = make_float2(s, s), t2 = make_float2(t, t);
+#pragma unroll 1
+        for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = ffma2(a[k], s2, t2);
+        }
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r += a[k].x + a[k].y;
+        sink[(long)blockIdx.x * blockDim.x + threadIdx.x] = r;
+    } else {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = 0.1f * (float)k;
+#pragma unroll 1
+        for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = fmaf(a[k], s, t);
+        }
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += a[k];
+        sink[(long)blockIdx.x * blockDim.x + threadIdx.x] = r;
+    }
+}
+
+}  // namespace tai
+
+using namespace tai;
+
+extern "C" int convlstm_gates_forward_b200(const float *conv_out, const float *state, float *new_state,
+                                           int B, int F, int HW, float forget_bias, void *stream)
+{
+    TAI_REQUIRE(conv_out && state && new_state && B > 0 && F > 0 && HW > 0, TAI_ERR_INVALID_ARGUMENT,
+                "convlstm_gates_forward_b200: bad arguments");
+    const long slab = (long)F * HW;
+    TAI_REQUIRE(fits_int31(4 * slab * B), TAI_ERR_TOO_LARGE, "convlstm_gates_forward_b200: tensor has >= 2^31 elements");
+    const bool vec = (slab % 4 == 0) && ((((uintptr_t)conv_out | (uintptr_t)state | (uintptr_t)new_state) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        gates_fwd_kernel<4><<<stream_grid(B * slab / 4, 256), 256, 0, st>>>(conv_out, state, new_state, B, slab, forget_bias);
+    else
+        gates_fwd_kernel<1><<<stream_grid(B * slab, 256), 256, 0, st>>>(conv_out, state, new_state, B, slab, forget_bias);
+    return check_launch("gates_fwd_kernel");
+}
+
+extern "C" int convlstm_gates_backward_b200(const float *conv_out, const float *state, const float *g_new_state,
+                                            float *g_conv_out, float *g_state,
+                                            int B, int F, int HW, float forget_bias, void *stream)
+{
+    TAI_REQUIRE(conv_out && state && g_new_state && g_conv_out && g_state && B > 0 && F > 0 && HW > 0,
+                TAI_ERR_INVALID_ARGUMENT, "convlstm_gates_backward_b200: bad arguments");
+    const long slab = (long)F * HW;
+    TAI_REQUIRE(fits_int31(4 * slab * B), TAI_ERR_TOO_LARGE, "convlstm_gates_backward_b200: tensor has >= 2^31 elements");
+    const bool vec = (slab % 4 == 0) &&
+                     ((((uintptr_t)conv_out | (uintptr_t)state | (uintptr_t)g_new_state | (uintptr_t)g_conv_out |
+                        (uintptr_t)g_state) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        gates_bwd_kernel<4><<<stream_grid(B * slab / 4, 256), 256, 0, st>>>(conv_out, state, g_new_state, g_conv_out, g_state, B, slab, forget_bias);
+    else
+        gates_bwd_kernel<1><<<stream_grid(B * slab, 256), 256, 0, st>>>(conv_out, state, g_new_state, g_conv_out, g_state, B, slab, forget_bias);
+    return check_launch("gates_bwd_kernel");
+}
+
+static int warp_args_ok(const char *who, int B, int C, int H, int W)
+{
+    TAI_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT, "%s: bad sizes B=%d C=%d H=%d W=%d", who, B, C, H, W);
+    TAI_REQUIRE(fits_int31((long long)B * (C > 2 ? C : 2) * H * W), TAI_ERR_TOO_LARGE, "%s: tensor has >= 2^31 elements", who);
+    return TAI_OK;
+}
+
+extern "C" int flow_warp_forward_b200(const float *img, const float *uv, float *out,
+                                      int B, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(img && uv && out, TAI_ERR_INVALID_ARGUMENT, "flow_warp_forward_b200: null pointer");
+    int rc = warp_args_ok("flow_warp_forward_b200", B, C, H, W);
+    if (rc) return rc;
+    warp_fwd_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, uv, out, B, C, H, W);
+    return check_launch("warp_fwd_kernel");
+}
+
+extern "C" int flow_warp_backward_b200(const float *img, const float *uv, const float *grad_out,
+                                       float *g_img, float *g_uv, int B, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(img && uv && grad_out && (g_img || g_uv), TAI_ERR_INVALID_ARGUMENT, "flow_warp_backward_b200: null pointer");
+    int rc = warp_args_ok("flow_warp_backward_b200", B, C, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_img) {
+        cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)B * C * H * W, st);
+        TAI_REQUIRE(e == cudaSuccess, TAI_ERR_CUDA, "flow_warp_backward_b200: memset: %s", cudaGetErrorString(e));
+    }
+    warp_bwd_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, H, W);
+    return check_launch("warp_bwd_kernel");
+}
+
+extern "C" int slomo_flow_combine_warp_forward_b200(const float *i0, const float *i1,
+                                                    const float *f01, const float *f10, double t,
+                                                    float *f_t0, float *f_t1, float *g0, float *g1,
+                                                    int B, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f01 && f10 && f_t0 && f_t1 && g0 && g1, TAI_ERR_INVALID_ARGUMENT,
+                "slomo_flow_combine_warp_forward_b200: null pointer");
+    int rc = warp_args_ok("slomo_flow_combine_warp_forward_b200", B, C, H, W);
+    if (rc) return rc;
+    // Python-float (double) scalars of slomo.py:313-314, rounded to FP32 when they meet the tensor.
+    const float c00 = (float)(-(1.0 - t) * t), c01 = (float)(t * t);
+    const float c10 = (float)((1.0 - t) * (1.0 - t)), c11 = (float)(t * (1.0 - t));
+    slomo_combine_warp_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+        i0, i1, f01, f10, c00, c01, c10, c11, f_t0, f_t1, g0, g1, B, C, H, W);
+    return check_launch("slomo_combine_warp_kernel");
+}
+
+extern "C" int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
+                                               const float *f_t0, const float *f_t1,
+                                               const float *d_t0, const float *d_t1, const float *v_t0,
+                                               double t, float *out, int B, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f_t0 && f_t1 && d_t0 && d_t1 && v_t0 && out, TAI_ERR_INVALID_ARGUMENT,
+                "slomo_refine_blend_forward_b200: null pointer");
+    int rc = warp_args_ok("slomo_refine_blend_forward_b200", B, C, H, W);
+    if (rc) return rc;
+    slomo_refine_blend_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+        i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, (float)(1.0 - t), (float)t, out, B, C, H, W);
+    return check_launch("slomo_refine_blend_kernel");
+}
+
+extern "C" int tai_b200_ffma_probe(float *sink, int grid, int block, int iters, int packed, void *stream)
+{
+    TAI_REQUIRE(sink && grid > 0 && block > 0 && block <= 1024 && iters > 0, TAI_ERR_INVALID_ARGUMENT,
+                "tai_b200_ffma_probe: bad arguments");
+    if (packed)
+        ffma_probe_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(sink, iters);
+    else
+        ffma_probe_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(sink, iters);
+    return check_launch("ffma_probe_kernel");
+}

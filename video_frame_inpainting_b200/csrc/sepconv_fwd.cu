@@ -1,0 +1,356 @@
+// Per-pixel separable local convolution, forward, for sm_100a.
+//
+//   O[b,c,y,x] = sum_i V[b,i,y,x] * ( sum_j H[b,j,y,x] * I[b,c,y+i,x+j] )
+//
+// (reference: src/separable_convolution/cfile/SeparableConvolution_kernel.cu:19-47, one thread per
+//  output element, 3 global loads per FMA).  This is an FP32 CUDA-core kernel: V and H differ for
+// every pixel, so there is no dense contraction to hand to the tensor cores.
+//
+// Work decomposition (all sizes compile-time except ks <= 4*J):
+//   * A warp owns NX=8 output columns x P=8 output rows.  Lane = (cx = lane&7, ch = lane>>3).
+//     Lane group `ch` owns the horizontal taps j == ch (mod 4): j = ch + 4*jj, jj < J.  It keeps those
+//     J taps of H for its P pixels in registers (J*P = 104 for ks=51), so every FMA of the inner
+//     product reads H from a register and I from shared memory.
+//   * The warp sweeps the ks+P-1 input rows that its P output rows touch.  One shared-memory word
+//     I[row][x+j] is loaded once per lane and reused by the P pixels of the thread (the P output
+//     rows see the same input row at P different vertical taps), i.e. P FMAs per LDS.  The four
+//     tap groups read x+ch+4*jj, which are consecutive words across a warp: conflict free.
+//   * Per (input row, pixel) the partial row sum s = sum_{j in group} H_j * I is multiplied by the
+//     pixel's vertical tap V_i (streamed from global, read once, the four tap-group lanes hit the
+//     same 32 B sector) and accumulated; the four tap groups are summed once per tile with two
+//     shuffles.
+//   * The (TILE_H+ks-1) x (TILE_W+ks-1) input halo of the block's tile is staged in shared memory;
+//     with PAD=true the replication pad of tai.py:170-171 is folded into that load (clamped
+//     coordinates), with DUAL=true the kernel filters both predictions and applies the blend of
+//     tai.py:105 / twi.py:105 in its epilogue.
+//
+// Algorithmic work per output element: 2*ks*ks flop (the ks extra vertical FMAs are not counted).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace tai {
+
+constexpr int FP = 8;   // output rows per thread
+constexpr int FNX = 8;  // output columns per warp
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+struct FwdParams {
+    const float *in[2];   // [B,C,Hi,Wi] (PAD: [B,C,Ho,Wo])
+    const float *ver[2];  // [B,ks,Ho,Wo]
+    const float *hor[2];
+    float *out[2];        // per-stream result (DUAL: dot1/dot2, may be null)
+    float *blend;         // DUAL only
+    float a, b;
+    int B, C, Ho, Wo, ks;
+    int ntx, nty;
+};
+
+// One input row of the sweep for output rows [RLO, RHI) of this thread.
+template <int J, int CG, int RLO, int RHI>
+__device__ __forceinline__ void fwd_row(const float *__restrict__ srow, int cstride,
+                                        const float *__restrict__ vp, long vstep,
+                                        const float (&h)[FP][J], float (&acc)[CG][FP])
+{
+    float v[FP];
+#pragma unroll
+    for (int r = RLO; r < RHI; ++r) v[r] = ld_stream(vp + r * vstep);
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+        float iv[J];
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) iv[jj] = srow[c * cstride + 4 * jj];
+#pragma unroll
+        for (int r = RLO; r < RHI; ++r) {
+            float s = h[r][0] * iv[0];
+#pragma unroll
+            for (int jj = 1; jj < J; ++jj) s = fmaf(h[r][jj], iv[jj], s);
+            acc[c][r] = fmaf(v[r], s, acc[c][r]);
+        }
+    }
+}
+
+template <int J, int CG, int WX, int WY, bool PAD, bool DUAL>
+__global__ void __launch_bounds__(32 * WX * WY, (CG == 1 ? 3 : 2))
+sepconv_fwd_kernel(const FwdParams p)
+{
+    constexpr int NT = 32 * WX * WY;
+    constexpr int TILE_W = WX * FNX, TILE_H = WY * FP;
+    constexpr int PITCH = TILE_W + 4 * J;
+    extern __shared__ float smem[];
+
+    const int ks = p.ks, Ho = p.Ho, Wo = p.Wo;
+    const int Hi = Ho + ks - 1, Wi = Wo + ks - 1;
+    const int rows = TILE_H + ks - 1;
+    const int cstride = rows * PITCH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = lane & 7, ch = lane >> 3;
+    const int wx = warp % WX, wy = warp / WX;
+
+    int t = blockIdx.x;
+    const int tx = t % p.ntx;
+    t /= p.ntx;
+    const int ty = t % p.nty;
+    const int b = t / p.nty;
+    // Tiles that would stick out are shifted back inside (their overlap recomputes identical values).
+    const int x0 = max(0, min(tx * TILE_W, Wo - TILE_W));
+    const int y0 = min(ty * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
+    const int px_raw = x0 + wx * FNX + cx;
+    const bool px_ok = px_raw < Wo;
+    const int px = px_ok ? px_raw : Wo - 1;
+    const int py0 = y0 + wy * FP;
+    const long plane = (long)Ho * Wo;
+    const long vstep = (long)Wo - plane;
+
+    float res[DUAL ? 2 : 1][CG][FP];
+
+    for (int c0 = 0; c0 < p.C; c0 += CG) {
+#pragma unroll
+        for (int s = 0; s < (DUAL ? 2 : 1); ++s) {
+            const float *__restrict__ in = p.in[s];
+            const float *__restrict__ ver = p.ver[s];
+            const float *__restrict__ hor = p.hor[s];
+
+            // ---- stage the input halo (replication pad folded in when PAD) ----
+            __syncthreads();
+            for (int c = 0; c < CG; ++c) {
+                const float *src = PAD ? in + ((long)(b * p.C + c0 + c)) * plane
+                                       : in + ((long)(b * p.C + c0 + c)) * Hi * Wi;
+                for (int ry = warp; ry < rows; ry += NT / 32) {
+                    const int gy = y0 + ry;
+                    for (int rx = lane; rx < PITCH; rx += 32) {
+                        const int gx = x0 + rx;
+                        float val = 0.f;
+                        if (rx < TILE_W + ks - 1) {
+                            if (PAD) {
+                                const int sy = clampi(gy - ks / 2, 0, Ho - 1);
+                                const int sx = clampi(gx - ks / 2, 0, Wo - 1);
+                                val = __ldg(src + (long)sy * Wo + sx);
+                            } else if (gx < Wi) {
+                                val = __ldg(src + (long)gy * Wi + gx);
+                            }
+                        }
+                        smem[c * cstride + ry * PITCH + rx] = val;
+                    }
+                }
+            }
+
+            // ---- this lane's horizontal taps for its P pixels ----
+            float h[FP][J];
+            {
+                const float *hp = hor + ((long)b * ks * Ho + py0) * Wo + px;
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    const int j = ch + 4 * jj;
+#pragma unroll
+                    for (int r = 0; r < FP; ++r)
+                        h[r][jj] = (j < ks) ? ld_stream(hp + (long)j * plane + (long)r * Wo) : 0.f;
+                }
+            }
+            __syncthreads();
+
+            float acc[CG][FP];
+#pragma unroll
+            for (int c = 0; c < CG; ++c)
+#pragma unroll
+                for (int r = 0; r < FP; ++r) acc[c][r] = 0.f;
+
+            const float *srow = smem + (wy * FP) * PITCH + wx * FNX + cx + ch;
+            const float *vp = ver + ((long)b * ks * Ho + py0) * Wo + px;  // tap 0, row py0
+
+            // prologue: input rows 0..P-2, output rows 0..yy are inside the kernel window
+            static_for<0, FP - 1>([&](auto YY) {
+                constexpr int yy = decltype(YY)::value;
+                fwd_row<J, CG, 0, yy + 1>(srow + yy * PITCH, cstride, vp + yy * plane, vstep, h, acc);
+            });
+            // steady state: every output row of the thread uses this input row
+#pragma unroll 1
+            for (int yy = FP - 1; yy < ks; ++yy)
+                fwd_row<J, CG, 0, FP>(srow + yy * PITCH, cstride, vp + yy * plane, vstep, h, acc);
+            // epilogue: input rows ks..ks+P-2
+            static_for<0, FP - 1>([&](auto E) {
+                constexpr int e = decltype(E)::value;
+                const int yy = ks + e;
+                fwd_row<J, CG, e + 1, FP>(srow + yy * PITCH, cstride, vp + yy * plane, vstep, h, acc);
+            });
+
+            // ---- sum the four tap groups ----
+#pragma unroll
+            for (int c = 0; c < CG; ++c)
+#pragma unroll
+                for (int r = 0; r < FP; ++r) {
+                    float a = acc[c][r];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    res[s][c][r] = a;
+                }
+        }
+
+        // ---- epilogue: stores (+ blend), lane group ch writes rows r == ch (mod 4) ----
+#pragma unroll
+        for (int c = 0; c < CG; ++c)
+#pragma unroll
+            for (int r = 0; r < FP; ++r) {
+                if ((r & 3) == ch && px_ok) {
+                    const long o = ((long)(b * p.C + c0 + c) * Ho + py0 + r) * Wo + px;
+                    if (DUAL) {
+                        if (p.out[0]) p.out[0][o] = res[0][c][r];
+                        if (p.out[1]) p.out[1][o] = res[DUAL ? 1 : 0][c][r];
+                        p.blend[o] = p.a * res[0][c][r] + p.b * res[DUAL ? 1 : 0][c][r];
+                    } else {
+                        p.out[0][o] = res[0][c][r];
+                    }
+                }
+            }
+    }
+}
+
+// Shape-agnostic fallback (tiny frames, ks < 8, ks > 64): one thread per output element, the
+// reference's loop nest with the replication pad / blend optionally fused.  Not a performance path.
+template <bool PAD, bool DUAL>
+__global__ void sepconv_fwd_simple_kernel(const FwdParams p)
+{
+    const int ks = p.ks, Ho = p.Ho, Wo = p.Wo;
+    const int Hi = Ho + ks - 1, Wi = Wo + ks - 1;
+    const long n = (long)p.B * p.C * Ho * Wo;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const int x = idx % Wo;
+        const int y = (idx / Wo) % Ho;
+        const int c = (idx / ((long)Wo * Ho)) % p.C;
+        const int b = idx / ((long)Wo * Ho * p.C);
+        float r[2] = {0.f, 0.f};
+        for (int s = 0; s < (DUAL ? 2 : 1); ++s) {
+            const float *in = p.in[s];
+            const float *ver = p.ver[s] + ((long)b * ks * Ho + y) * Wo + x;
+            const float *hor = p.hor[s] + ((long)b * ks * Ho + y) * Wo + x;
+            float acc = 0.f;
+            for (int i = 0; i < ks; ++i) {
+                float rs = 0.f;
+                for (int j = 0; j < ks; ++j) {
+                    float iv;
+                    if (PAD) {
+                        const int sy = clampi(y + i - ks / 2, 0, Ho - 1);
+                        const int sx = clampi(x + j - ks / 2, 0, Wo - 1);
+                        iv = in[((long)(b * p.C + c) * Ho + sy) * Wo + sx];
+                    } else {
+                        iv = in[((long)(b * p.C + c) * Hi + y + i) * Wi + x + j];
+                    }
+                    rs = fmaf(hor[(long)j * Ho * Wo], iv, rs);
+                }
+                acc = fmaf(ver[(long)i * Ho * Wo], rs, acc);
+            }
+            r[s] = acc;
+        }
+        if (DUAL) {
+            if (p.out[0]) p.out[0][idx] = r[0];
+            if (p.out[1]) p.out[1][idx] = r[1];
+            p.blend[idx] = p.a * r[0] + p.b * r[1];
+        } else {
+            p.out[0][idx] = r[0];
+        }
+    }
+}
+
+template <int J, int CG, bool PAD, bool DUAL>
+static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
+{
+    constexpr int WX = 4, WY = 1;
+    constexpr int TILE_W = WX * FNX, TILE_H = WY * FP;
+    constexpr int PITCH = TILE_W + 4 * J;
+    FwdParams p = p0;
+    p.ntx = ceil_div(p.Wo, TILE_W);
+    p.nty = ceil_div(p.Ho, TILE_H);
+    const size_t smem = (size_t)CG * (TILE_H + p.ks - 1) * PITCH * sizeof(float);
+    auto kern = sepconv_fwd_kernel<J, CG, WX, WY, PAD, DUAL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_done = true;
+    }
+    const long blocks = (long)p.B * p.nty * p.ntx;
+    kern<<<(unsigned)blocks, 32 * WX * WY, smem, st>>>(p);
+    return check_launch("sepconv_fwd_kernel");
+}
+
+template <bool PAD, bool DUAL>
+static int launch_fwd(const FwdParams &p, cudaStream_t st)
+{
+    const int ks = p.ks;
+    const bool tiled = ks >= FP && ks <= 64 && p.Ho >= FP;
+    if (!tiled) {
+        const long n = (long)p.B * p.C * p.Ho * p.Wo;
+        const int block = 128;
+        const long grid = (n + block - 1) / block;
+        sepconv_fwd_simple_kernel<PAD, DUAL><<<(unsigned)(grid < 1 ? 1 : grid), block, 0, st>>>(p);
+        return check_launch("sepconv_fwd_simple_kernel");
+    }
+    const int j = ceil_div(ks, 4);
+    const bool c3 = (p.C % 3 == 0);
+#define TAI_FWD_CASE(JJ)                                                  \
+    if (j <= JJ)                                                          \
+        return c3 ? launch_fwd_tiled<JJ, 3, PAD, DUAL>(p, st) : launch_fwd_tiled<JJ, 1, PAD, DUAL>(p, st);
+    TAI_FWD_CASE(4)
+    TAI_FWD_CASE(7)
+    TAI_FWD_CASE(10)
+    TAI_FWD_CASE(13)
+    TAI_FWD_CASE(16)
+#undef TAI_FWD_CASE
+    set_error("sepconv forward: ks=%d unsupported", ks);
+    return TAI_ERR_UNSUPPORTED;
+}
+
+}  // namespace tai
+
+using namespace tai;
+
+extern "C" int SeparableConvolution_cuda_forward_b200(const float *input, const float *vertical,
+                                                      const float *horizontal, float *output,
+                                                      int B, int C, int Hi, int Wi, int ks, void *stream)
+{
+    TAI_REQUIRE(input && vertical && horizontal && output, TAI_ERR_INVALID_ARGUMENT,
+                "SeparableConvolution_cuda_forward_b200: null pointer");
+    TAI_REQUIRE(B > 0 && C > 0 && ks > 0 && Hi >= ks && Wi >= ks, TAI_ERR_INVALID_ARGUMENT,
+                "SeparableConvolution_cuda_forward_b200: bad sizes B=%d C=%d Hi=%d Wi=%d ks=%d", B, C, Hi, Wi, ks);
+    const int Ho = Hi - ks + 1, Wo = Wi - ks + 1;
+    TAI_REQUIRE(fits_int31((long long)B * C * Hi * Wi) && fits_int31((long long)B * ks * Ho * Wo),
+                TAI_ERR_TOO_LARGE, "SeparableConvolution_cuda_forward_b200: tensor has >= 2^31 elements");
+    FwdParams p{};
+    p.in[0] = input;
+    p.ver[0] = vertical;
+    p.hor[0] = horizontal;
+    p.out[0] = output;
+    p.B = B; p.C = C; p.Ho = Ho; p.Wo = Wo; p.ks = ks;
+    return launch_fwd<false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int tai_fused_forward_b200(const float *pred_f, const float *pred_b,
+                                      const float *v1, const float *h1, const float *v2, const float *h2,
+                                      float *pred, float *dot1, float *dot2,
+                                      int B, int C, int H, int W, int ks, float a, float b, void *stream)
+{
+    TAI_REQUIRE(pred_f && pred_b && v1 && h1 && v2 && h2 && pred, TAI_ERR_INVALID_ARGUMENT,
+                "tai_fused_forward_b200: null pointer");
+    TAI_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && ks > 0, TAI_ERR_INVALID_ARGUMENT,
+                "tai_fused_forward_b200: bad sizes B=%d C=%d H=%d W=%d ks=%d", B, C, H, W, ks);
+    TAI_REQUIRE((ks & 1) == 1, TAI_ERR_INVALID_ARGUMENT,
+                "tai_fused_forward_b200: ks=%d must be odd (symmetric replication pad, tai.py:170)", ks);
+    TAI_REQUIRE(fits_int31((long long)B * ks * H * W) && fits_int31((long long)B * C * (H + ks) * (W + ks)),
+                TAI_ERR_TOO_LARGE, "tai_fused_forward_b200: tensor has >= 2^31 elements");
+    FwdParams p{};
+    p.in[0] = pred_f; p.in[1] = pred_b;
+    p.ver[0] = v1; p.ver[1] = v2;
+    p.hor[0] = h1; p.hor[1] = h2;
+    p.out[0] = dot1; p.out[1] = dot2;
+    p.blend = pred;
+    p.a = a; p.b = b;
+    p.B = B; p.C = C; p.Ho = H; p.Wo = W; p.ks = ks;
+    return launch_fwd<true, true>(p, (cudaStream_t)stream);
+}

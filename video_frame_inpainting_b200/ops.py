@@ -1,0 +1,304 @@
+"""Tensor-level wrappers over the C ABI (include/tai_b200.h) and their autograd Functions.
+
+torch is used here for device memory, streams and autograd bookkeeping only; all arithmetic of the
+hot path happens in libtai_b200.so.  CPU tensors raise NotImplementedError exactly like the reference
+operator (src/separable_convolution/SeparableConvolution.py:48-49,86-87) -- there is no fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(name, *tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NotImplementedError("%s: CPU tensors are not supported (no CPU version, as in the reference)" % name)
+        if t.dtype != torch.float32:
+            raise TypeError("%s: expected float32 tensors, got %s" % (name, t.dtype))
+        assert t.is_contiguous(), "%s: tensors must be contiguous" % name
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("%s: tensors live on different devices" % name)
+    return dev
+
+
+# ------------------------------------------------------------------------------------------------
+# separable convolution
+# ------------------------------------------------------------------------------------------------
+
+def sepconv_shapes(input, vertical, horizontal, ks):
+    """The shape algebra and asserts of SeparableConvolution.py:16-33."""
+    B, C, Hi, Wi = input.shape
+    fs = min(vertical.size(1), horizontal.size(1))
+    Ho = min(vertical.size(2), horizontal.size(2))
+    Wo = min(vertical.size(3), horizontal.size(3))
+    assert Hi - ks == Ho - 1
+    assert Wi - ks == Wo - 1
+    assert fs == ks
+    assert vertical.shape == horizontal.shape == (B, ks, Ho, Wo), \
+        "vertical/horizontal must both be [B, ks, Ho, Wo]"
+    return B, C, Hi, Wi, Ho, Wo
+
+
+def sepconv_forward(input, vertical, horizontal, ks):
+    dev = _check("sepconv_forward", input, vertical, horizontal)
+    B, C, Hi, Wi, Ho, Wo = sepconv_shapes(input, vertical, horizontal, ks)
+    with torch.cuda.device(dev):
+        out = torch.empty((B, C, Ho, Wo), device=dev, dtype=torch.float32)
+        _lib.call("SeparableConvolution_cuda_forward_b200", _ptr(input), _ptr(vertical), _ptr(horizontal),
+                  _ptr(out), B, C, Hi, Wi, ks, _stream())
+    return out
+
+
+def sepconv_backward(grad_output, input, vertical, horizontal, ks, needs=(True, True, True)):
+    dev = _check("sepconv_backward", grad_output, input, vertical, horizontal)
+    B, C, Hi, Wi, Ho, Wo = sepconv_shapes(input, vertical, horizontal, ks)
+    assert grad_output.shape == (B, C, Ho, Wo)
+    with torch.cuda.device(dev):
+        gi = torch.empty_like(input) if needs[0] else None
+        gv = torch.empty_like(vertical) if needs[1] else None
+        gh = torch.empty_like(horizontal) if needs[2] else None
+        if any(needs):
+            _lib.call("SeparableConvolution_cuda_backward_b200", _ptr(grad_output), _ptr(input), _ptr(vertical),
+                      _ptr(horizontal), _ptr(gi), _ptr(gv), _ptr(gh), B, C, Hi, Wi, ks, _stream())
+    return gi, gv, gh
+
+
+def tai_fused_forward(pred_f, pred_b, v1, h1, v2, h2, ks, a=0.5, b=0.5, emit_intermediate=True):
+    """pad + 2 x sepconv + blend (tai.py:229-236,105).  Returns (pred, dot1, dot2); dot1/dot2 are None
+    when emit_intermediate is False."""
+    dev = _check("tai_fused_forward", pred_f, pred_b, v1, h1, v2, h2)
+    B, C, H, W = pred_f.shape
+    assert pred_b.shape == pred_f.shape
+    for k in (v1, h1, v2, h2):
+        assert k.shape == (B, ks, H, W), "kernel maps must be [B, ks, H, W]"
+    with torch.cuda.device(dev):
+        pred = torch.empty_like(pred_f)
+        d1 = torch.empty_like(pred_f) if emit_intermediate else None
+        d2 = torch.empty_like(pred_f) if emit_intermediate else None
+        _lib.call("tai_fused_forward_b200", _ptr(pred_f), _ptr(pred_b), _ptr(v1), _ptr(h1), _ptr(v2), _ptr(h2),
+                  _ptr(pred), _ptr(d1), _ptr(d2), B, C, H, W, ks, float(a), float(b), _stream())
+    return pred, d1, d2
+
+
+def tai_fused_backward(g_pred, g_dot1, g_dot2, pred_f, pred_b, v1, h1, v2, h2, ks, a, b,
+                       need_pred=(True, True), need_maps=True):
+    dev = _check("tai_fused_backward", g_pred, g_dot1, g_dot2, pred_f, pred_b, v1, h1, v2, h2)
+    B, C, H, W = pred_f.shape
+    with torch.cuda.device(dev):
+        ws_bytes = _lib.load().tai_fused_backward_workspace_bytes(B, C, H, W, ks)
+        ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32)
+        gpf = torch.empty_like(pred_f) if need_pred[0] else None
+        gpb = torch.empty_like(pred_b) if need_pred[1] else None
+        gv1, gh1, gv2, gh2 = (torch.empty_like(v1) if need_maps else None for _ in range(4))
+        _lib.call("tai_fused_backward_b200", _ptr(g_pred), _ptr(g_dot1), _ptr(g_dot2), _ptr(pred_f), _ptr(pred_b),
+                  _ptr(v1), _ptr(h1), _ptr(v2), _ptr(h2), _ptr(gpf), _ptr(gpb), _ptr(gv1), _ptr(gh1), _ptr(gv2),
+                  _ptr(gh2), _ptr(ws), B, C, H, W, ks, float(a), float(b), _stream())
+    return gpf, gpb, gv1, gh1, gv2, gh2
+
+
+def replication_pad_forward(x, p):
+    dev = _check("replication_pad_forward", x)
+    H, W = x.shape[-2:]
+    N = x.numel() // (H * W)
+    with torch.cuda.device(dev):
+        out = torch.empty(x.shape[:-2] + (H + 2 * p, W + 2 * p), device=dev, dtype=torch.float32)
+        _lib.call("replication_pad_forward_b200", _ptr(x), _ptr(out), N, H, W, p, _stream())
+    return out
+
+
+def replication_pad_backward(g, p):
+    dev = _check("replication_pad_backward", g)
+    Hp, Wp = g.shape[-2:]
+    H, W = Hp - 2 * p, Wp - 2 * p
+    N = g.numel() // (Hp * Wp)
+    with torch.cuda.device(dev):
+        out = torch.empty(g.shape[:-2] + (H, W), device=dev, dtype=torch.float32)
+        _lib.call("replication_pad_backward_b200", _ptr(g), _ptr(out), N, H, W, p, _stream())
+    return out
+
+
+class SeparableConvolutionFunction(torch.autograd.Function):
+    """autograd.Function with the reference's contract (SeparableConvolution.py:6-92):
+    apply(input, vertical, horizontal, ks) -> output; backward -> (gI, gV, gH, None); gradients are
+    not differentiable (no double backward)."""
+
+    @staticmethod
+    def forward(ctx, input, vertical, horizontal, ks=51):
+        ctx.save_for_backward(input, vertical, horizontal)
+        ctx.constant = ks
+        return sepconv_forward(input, vertical, horizontal, ks)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, vertical, horizontal = ctx.saved_tensors
+        gi, gv, gh = sepconv_backward(grad_output.contiguous(), input, vertical, horizontal, ctx.constant,
+                                      needs=tuple(ctx.needs_input_grad[:3]))
+        return gi, gv, gh, None
+
+
+class TAIBlendSepConvFunction(torch.autograd.Function):
+    """Fused pad + sepconv x2 + blend.  apply(pred_f, pred_b, v1, h1, v2, h2, ks, a, b) ->
+    (pred, dot1, dot2)."""
+
+    @staticmethod
+    def forward(ctx, pred_f, pred_b, v1, h1, v2, h2, ks, a, b):
+        ctx.save_for_backward(pred_f, pred_b, v1, h1, v2, h2)
+        ctx.consts = (ks, float(a), float(b))
+        ctx.set_materialize_grads(False)
+        return tai_fused_forward(pred_f, pred_b, v1, h1, v2, h2, ks, a, b, emit_intermediate=True)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_pred, g_dot1, g_dot2):
+        pred_f, pred_b, v1, h1, v2, h2 = ctx.saved_tensors
+        ks, a, b = ctx.consts
+        if g_pred is None and g_dot1 is None and g_dot2 is None:
+            return (None,) * 9
+        cont = lambda g: None if g is None else g.contiguous()
+        need = ctx.needs_input_grad
+        gpf, gpb, gv1, gh1, gv2, gh2 = tai_fused_backward(
+            cont(g_pred), cont(g_dot1), cont(g_dot2), pred_f, pred_b, v1, h1, v2, h2, ks, a, b,
+            need_pred=(need[0], need[1]), need_maps=any(need[2:6]))
+        return gpf, gpb, gv1, gh1, gv2, gh2, None, None, None
+
+
+def tai_blend_sepconv(pred_f, pred_b, v1, h1, v2, h2, ks, a=0.5, b=0.5, emit_intermediate=True):
+    """Public fused entry.  Differentiable; returns (pred, dot1, dot2)."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (pred_f, pred_b, v1, h1, v2, h2)):
+        return TAIBlendSepConvFunction.apply(pred_f, pred_b, v1, h1, v2, h2, ks, a, b)
+    return tai_fused_forward(pred_f, pred_b, v1, h1, v2, h2, ks, a, b, emit_intermediate)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvLSTM gates
+# ------------------------------------------------------------------------------------------------
+
+def convlstm_gates_forward(conv_out, state, forget_bias=1.0):
+    dev = _check("convlstm_gates_forward", conv_out, state)
+    B, F2 = state.shape[:2]
+    assert F2 % 2 == 0 and conv_out.shape[1] == 2 * F2 and conv_out.shape[0] == B
+    assert conv_out.shape[2:] == state.shape[2:]
+    F = F2 // 2
+    HW = state.numel() // (B * F2)
+    with torch.cuda.device(dev):
+        new_state = torch.empty_like(state)
+        _lib.call("convlstm_gates_forward_b200", _ptr(conv_out), _ptr(state), _ptr(new_state), B, F, HW,
+                  float(forget_bias), _stream())
+    return new_state
+
+
+def convlstm_gates_backward(conv_out, state, g_new_state, forget_bias=1.0):
+    dev = _check("convlstm_gates_backward", conv_out, state, g_new_state)
+    B, F2 = state.shape[:2]
+    F = F2 // 2
+    HW = state.numel() // (B * F2)
+    with torch.cuda.device(dev):
+        g_conv = torch.empty_like(conv_out)
+        g_state = torch.empty_like(state)
+        _lib.call("convlstm_gates_backward_b200", _ptr(conv_out), _ptr(state), _ptr(g_new_state), _ptr(g_conv),
+                  _ptr(g_state), B, F, HW, float(forget_bias), _stream())
+    return g_conv, g_state
+
+
+class ConvLstmGatesFunction(torch.autograd.Function):
+    """apply(conv_out, state, forget_bias) -> new_state = cat(c', h')   (mcnet.py:287-293)."""
+
+    @staticmethod
+    def forward(ctx, conv_out, state, forget_bias):
+        ctx.save_for_backward(conv_out, state)
+        ctx.forget_bias = float(forget_bias)
+        return convlstm_gates_forward(conv_out, state, forget_bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_new_state):
+        conv_out, state = ctx.saved_tensors
+        g_conv, g_state = convlstm_gates_backward(conv_out, state, g_new_state.contiguous(), ctx.forget_bias)
+        return g_conv, g_state, None
+
+
+# ------------------------------------------------------------------------------------------------
+# Super SloMo warp / blend
+# ------------------------------------------------------------------------------------------------
+
+def flow_warp_forward(img, uv):
+    dev = _check("flow_warp_forward", img, uv)
+    B, C, H, W = img.shape
+    assert uv.shape == (B, 2, H, W)
+    with torch.cuda.device(dev):
+        out = torch.empty_like(img)
+        _lib.call("flow_warp_forward_b200", _ptr(img), _ptr(uv), _ptr(out), B, C, H, W, _stream())
+    return out
+
+
+def flow_warp_backward(img, uv, grad_out, need_img=True, need_uv=True):
+    dev = _check("flow_warp_backward", img, uv, grad_out)
+    B, C, H, W = img.shape
+    with torch.cuda.device(dev):
+        g_img = torch.empty_like(img) if need_img else None
+        g_uv = torch.empty_like(uv) if need_uv else None
+        if need_img or need_uv:
+            _lib.call("flow_warp_backward_b200", _ptr(img), _ptr(uv), _ptr(grad_out), _ptr(g_img), _ptr(g_uv),
+                      B, C, H, W, _stream())
+    return g_img, g_uv
+
+
+class FlowWarpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, uv):
+        ctx.save_for_backward(img, uv)
+        return flow_warp_forward(img, uv)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        img, uv = ctx.saved_tensors
+        return flow_warp_backward(img, uv, grad_out.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+def slomo_flow_combine_warp(i0, i1, f01, f10, t):
+    """slomo.py:312-316 fused: returns (F_t_0, F_t_1, g_I0_F_t_0, g_I1_F_t_1).  Forward only."""
+    dev = _check("slomo_flow_combine_warp", i0, i1, f01, f10)
+    B, C, H, W = i0.shape
+    assert i1.shape == i0.shape and f01.shape == f10.shape == (B, 2, H, W)
+    with torch.cuda.device(dev):
+        ft0, ft1 = torch.empty_like(f01), torch.empty_like(f01)
+        g0, g1 = torch.empty_like(i0), torch.empty_like(i0)
+        _lib.call("slomo_flow_combine_warp_forward_b200", _ptr(i0), _ptr(i1), _ptr(f01), _ptr(f10), float(t),
+                  _ptr(ft0), _ptr(ft1), _ptr(g0), _ptr(g1), B, C, H, W, _stream())
+    return ft0, ft1, g0, g1
+
+
+def slomo_refine_blend(i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, t):
+    """slomo.py:320-328 fused: returns the interpolated frame.  Forward only."""
+    dev = _check("slomo_refine_blend", i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0)
+    B, C, H, W = i0.shape
+    assert v_t0.shape == (B, 1, H, W)
+    with torch.cuda.device(dev):
+        out = torch.empty_like(i0)
+        _lib.call("slomo_refine_blend_forward_b200", _ptr(i0), _ptr(i1), _ptr(f_t0), _ptr(f_t1), _ptr(d_t0),
+                  _ptr(d_t1), _ptr(v_t0), float(t), _ptr(out), B, C, H, W, _stream())
+    return out
+
+
+def ffma_probe(grid, block, iters, packed=False):
+    """Launch the pure-FFMA probe kernel; returns the sink tensor (flops = 2*8*iters*grid*block)."""
+    sink = torch.empty(grid * block, device="cuda", dtype=torch.float32)
+    _lib.call("tai_b200_ffma_probe", _ptr(sink), grid, block, iters, int(bool(packed)), _stream())
+    return sink
