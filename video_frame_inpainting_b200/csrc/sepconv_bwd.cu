@@ -8,23 +8,11 @@
 // Here gV and gH come out of ONE pass over the window (the same LDS of I feeds both), with the
 // lane layout of the forward kernel; gI is a separate gather kernel.
 #include "common.cuh"
+#include "sepconv_bwd_vh_v3.cuh"
 
 namespace tai {
 
-constexpr int BP = 4;   // output rows per thread in the gV/gH kernel
 constexpr int BNX = 8;  // output columns per warp
-
-struct BwdParams {
-    const float *gout;  // [B,C,Ho,Wo]
-    const float *in;    // [B,C,Hi,Wi] (PAD: [B,C,Ho,Wo])
-    const float *ver;   // [B,ks,Ho,Wo]
-    const float *hor;
-    float *gver;        // [B,ks,Ho,Wo] or null
-    float *ghor;        // [B,ks,Ho,Wo] or null
-    float *gin;         // [B,C,Hi,Wi] or null
-    int B, C, Ho, Wo, ks;
-    int ntx, nty;
-};
 
 // ------------------------------------------------------------------------------------------------
 // gV + gH.  A warp owns 8 columns x BP rows; lane = (cx = lane&7, ch = lane>>3); lane group ch owns
@@ -346,6 +334,43 @@ static int launch_vh_tiled(const BwdParams &p0, cudaStream_t st)
     return check_launch("sepconv_bwd_vh_kernel");
 }
 
+// Persistent TMA-fed gV+gH kernel (sepconv_bwd_vh_v3.cuh); +1 = shape not TMA-describable, fall back.
+template <int KS, int CG, bool PAD>
+static int launch_vh_v3(const BwdParams &p0, cudaStream_t st)
+{
+    using Cfg = VhV3Cfg<KS>;
+    BwdParams p = p0;
+    VhV3Maps maps;
+    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+        !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
+        return 1;
+    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
+    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
+    auto kern = sepconv_bwd_vh_v3_kernel<KS, CG, PAD>;
+    const size_t smem = Cfg::smem_bytes(CG);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    long ctas = (long)p.B * p.nty * p.ntx;
+    const long resident = (long)sm_count() * ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    return check_launch("sepconv_bwd_vh_v3_kernel");
+}
+
+template <int KS, bool PAD>
+static int launch_vh_v3_c(const BwdParams &p, cudaStream_t st)
+{
+    return p.C == 3 ? launch_vh_v3<KS, 3, PAD>(p, st) : launch_vh_v3<KS, 1, PAD>(p, st);
+}
+
 template <bool PAD>
 static int launch_vh(const BwdParams &p, cudaStream_t st)
 {
@@ -355,6 +380,17 @@ static int launch_vh(const BwdParams &p, cudaStream_t st)
         const long n = (long)p.B * ks * p.Ho * p.Wo;
         sepconv_bwd_vh_simple_kernel<PAD><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
         return check_launch("sepconv_bwd_vh_simple_kernel");
+    }
+    {
+        int rc = 1;
+        switch (ks) {
+            case 51: rc = launch_vh_v3_c<51, PAD>(p, st); break;
+            case 37: rc = launch_vh_v3_c<37, PAD>(p, st); break;
+            case 25: rc = launch_vh_v3_c<25, PAD>(p, st); break;
+            case 13: rc = launch_vh_v3_c<13, PAD>(p, st); break;
+            default: break;
+        }
+        if (rc <= 0) return rc;
     }
     const int j = ceil_div(ks, 4);
 #define TAI_VH_CASE(JJ) \

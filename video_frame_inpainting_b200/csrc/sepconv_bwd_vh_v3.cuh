@@ -1,0 +1,280 @@
+// Gradients of the separable convolution w.r.t. both kernel maps, one pass, for sm_100a
+// (persistent, TMA-fed; compile-time ks).
+//
+//   gV[b,i,y,x] = sum_c gO[b,c,y,x] * sum_j H[b,j,y,x] * I[b,c,y+i,x+j]            (kernel.cu:49-86)
+//   gH[b,j,y,x] = sum_c gO[b,c,y,x] * sum_i V[b,i,y,x] * I[b,c,y+i,x+j]            (kernel.cu:88-118)
+//
+// The reference walks the ks x ks window twice (two kernels, one thread per output element).  Here one
+// sweep produces both: a warp owns 8 columns x 4 rows, lane = (cx = lane&7, ch = lane>>3), lane group ch
+// owns the horizontal taps j == ch (mod 4).  Per input row yy and output row r (vertical tap i = yy-r):
+//     s_r     = sum_{j in group} H_j * I[yy][x+j]      -> gV_i = sum_c gO_c * (s_r summed over the 4 groups)
+//     a_r[j] += (V_i * gO_c) * I[yy][x+j]               -> gH_j, complete inside the lane
+// The same shared-memory word of I feeds both FMAs.  The four partial s_r are combined by a 3-shuffle
+// reduce-scatter after which lane group ch holds the total of output row r = ch and stores it.
+// Data movement is that of sepconv_fwd_v3.cuh: H box -> slab (TMA) -> registers, slab refilled with the
+// V box in three tap chunks, next tile's boxes prefetched into L2, halo staged by LDG/STS with the
+// replication pad optionally folded in.
+#pragma once
+
+#include "common.cuh"
+#include "sepconv_common.cuh"
+#include "tma.cuh"
+
+namespace tai {
+
+constexpr int BP = 4;  // output rows per thread
+
+struct BwdParams {
+    const float *gout;  // [B,C,Ho,Wo]
+    const float *in;    // [B,C,Hi,Wi] (PAD: [B,C,Ho,Wo])
+    const float *ver;   // [B,ks,Ho,Wo]
+    const float *hor;
+    float *gver;        // [B,ks,Ho,Wo] or null
+    float *ghor;        // [B,ks,Ho,Wo] or null
+    float *gin;         // [B,C,Hi,Wi] or null
+    int B, C, Ho, Wo, ks;
+    int ntx, nty;
+};
+
+template <int KS>
+struct VhV3Cfg {
+    static constexpr int J = (KS + 3) / 4;
+    static constexpr int WX = 4;
+    static constexpr int NT = 32 * WX;
+    static constexpr int TILE_W = WX * FNX, TILE_H = BP;
+    static constexpr int PITCH = TILE_W + 4 * J;
+    static constexpr int ROWS = TILE_H + KS - 1;
+    static constexpr int NCHUNK = 3;
+    static constexpr int CH_TAPS = (KS + NCHUNK - 1) / NCHUNK;
+    static constexpr int VROW = TILE_H * TILE_W;
+    static constexpr int SLAB_FLOATS = NCHUNK * CH_TAPS * VROW;
+    static constexpr int NBAR = 1 + NCHUNK;
+    static constexpr size_t smem_bytes(int cg) { return (size_t)(SLAB_FLOATS + cg * ROWS * PITCH) * 4 + 8 * NBAR; }
+};
+
+struct VhV3Maps {
+    CUtensorMap h;  // box {32, 4, KS, 1}
+    CUtensorMap v;  // box {32, 4, CH_TAPS, 1}
+};
+
+// One input row: output rows [RLO, RHI) of this thread are inside the kernel window.
+template <int KS, int CG, int RLO, int RHI>
+__device__ __forceinline__ void vh_row_v3(const float *__restrict__ srow, const float *__restrict__ vrow,
+                                          const float (&h)[BP][(KS + 3) / 4], float (&a)[BP][(KS + 3) / 4],
+                                          const float (&go)[CG][BP], float (&tsum)[BP])
+{
+    using Cfg = VhV3Cfg<KS>;
+    constexpr int J = Cfg::J;
+    constexpr int CSTRIDE = Cfg::ROWS * Cfg::PITCH;
+    float v[BP];
+#pragma unroll
+    for (int r = 0; r < BP; ++r) {
+        v[r] = (r >= RLO && r < RHI) ? vrow[r * (Cfg::TILE_W - Cfg::VROW)] : 0.f;  // tap yy-r, output row r
+        tsum[r] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+        float iv[J];
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) iv[jj] = srow[c * CSTRIDE + 4 * jj];
+#pragma unroll
+        for (int r = RLO; r < RHI; ++r) {
+            const float w = v[r] * go[c][r];
+            float s = h[r][0] * iv[0];
+            a[r][0] = fmaf(w, iv[0], a[r][0]);
+#pragma unroll
+            for (int jj = 1; jj < J; ++jj) {
+                s = fmaf(h[r][jj], iv[jj], s);
+                a[r][jj] = fmaf(w, iv[jj], a[r][jj]);
+            }
+            tsum[r] = fmaf(go[c][r], s, tsum[r]);
+        }
+    }
+}
+
+template <int KS, int CG, bool PAD>
+__global__ void __launch_bounds__(128, 3)
+sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams p)
+{
+    static_assert(BP == 4, "the reduce-scatter assumes 4 output rows == 4 tap groups");
+    using Cfg = VhV3Cfg<KS>;
+    constexpr int J = Cfg::J, PITCH = Cfg::PITCH, ROWS = Cfg::ROWS, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
+    constexpr int CSTRIDE = ROWS * PITCH;
+    extern __shared__ __align__(128) float smem[];
+    float *slab = smem;
+    float *is = smem + Cfg::SLAB_FLOATS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(is + CG * CSTRIDE);
+
+    const int Ho = p.Ho, Wo = p.Wo;
+    const int Hi = Ho + KS - 1, Wi = Wo + KS - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = lane & 7, ch = lane >> 3;
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+    const long plane = (long)Ho * Wo;
+    const int ntiles = p.B * p.nty * p.ntx;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.ntx;
+        t /= p.ntx;
+        const int ty = t % p.nty;
+        const int b = t / p.nty;
+        const int x0 = max(0, min(tx * TILE_W, Wo - TILE_W));
+        const int y0 = min(ty * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
+        const int px_raw = x0 + warp * FNX + cx;
+        const bool px_ok = px_raw < Wo;
+        const int px = px_ok ? px_raw : Wo - 1;
+
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
+            tma_load_4d(slab, &maps.h, &bars[0], x0, y0, 0, b);
+        }
+        // ---- halo of all CG (== C) channels ----
+        {
+            constexpr int NK = (PITCH + 31) / 32;
+            constexpr int RB = 4;
+            int coff[NK];
+            bool cok[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const int rx = lane + 32 * k, gx = x0 + rx;
+                if (PAD) {
+                    cok[k] = rx < TILE_W + KS - 1;
+                    coff[k] = clampi(gx - KS / 2, 0, Wo - 1);
+                } else {
+                    cok[k] = rx < TILE_W + KS - 1 && gx < Wi;
+                    coff[k] = cok[k] ? gx : 0;
+                }
+            }
+            for (int c = 0; c < CG; ++c) {
+                const float *src = PAD ? p.in + ((long)(b * CG + c)) * plane : p.in + ((long)(b * CG + c)) * Hi * Wi;
+                for (int ry0 = warp * RB; ry0 < ROWS; ry0 += (Cfg::NT / 32) * RB) {
+                    float tmp[RB][NK];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const int gy = y0 + min(ry0 + q, ROWS - 1);
+                        const float *grow = PAD ? src + (long)clampi(gy - KS / 2, 0, Ho - 1) * Wo : src + (long)gy * Wi;
+#pragma unroll
+                        for (int k = 0; k < NK; ++k) tmp[q][k] = cok[k] ? __ldg(grow + coff[k]) : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        if (ry0 + q < ROWS) {
+                            float *drow = is + c * CSTRIDE + (ry0 + q) * PITCH + lane;
+#pragma unroll
+                            for (int k = 0; k < NK; ++k)
+                                if (lane + 32 * k < PITCH) drow[32 * k] = tmp[q][k];
+                        }
+                    }
+                }
+            }
+        }
+        float go[CG][BP];
+#pragma unroll
+        for (int c = 0; c < CG; ++c)
+#pragma unroll
+            for (int r = 0; r < BP; ++r) go[c][r] = __ldg(p.gout + ((long)(b * CG + c) * Ho + y0 + r) * Wo + px);
+
+        // ---- H taps: slab -> registers ----
+        mbar_wait(&bars[0], parity);
+        float h[BP][J], a[BP][J];
+        {
+            const float *hs = slab + ch * Cfg::VROW + warp * FNX + cx;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj)
+#pragma unroll
+                for (int r = 0; r < BP; ++r) {
+                    h[r][jj] = (ch + 4 * jj < KS) ? hs[(4 * jj) * Cfg::VROW + r * TILE_W] : 0.f;
+                    a[r][jj] = 0.f;
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+#pragma unroll
+            for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                mbar_expect_tx(&bars[1 + q], Cfg::CH_TAPS * Cfg::VROW * 4);
+                tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v, &bars[1 + q], x0, y0, q * Cfg::CH_TAPS, b);
+            }
+            if (tile + (int)gridDim.x < ntiles) {
+                int n = tile + gridDim.x;
+                const int ntx_ = n % p.ntx;
+                n /= p.ntx;
+                const int nty_ = n % p.nty;
+                const int nb = n / p.nty;
+                const int nx0 = max(0, min(ntx_ * TILE_W, Wo - TILE_W)), ny0 = min(nty_ * TILE_H, Ho - TILE_H);
+                tma_prefetch_l2_4d(&maps.h, nx0, ny0, 0, nb);
+#pragma unroll
+                for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
+            }
+        }
+
+        const float *srow = is + warp * FNX + cx + ch;
+        const float *vrow = slab + warp * FNX + cx;
+        float *gv = p.gver ? p.gver + ((long)b * KS * Ho + y0 + ch) * Wo + px : nullptr;  // + tap * plane
+
+        // After one input row: combine the four tap groups and store gV[tap yy-ch][row ch].
+        auto finish_row = [&](int yy, float (&tsum)[BP]) {
+            const float keep0 = hi16 ? tsum[2] : tsum[0];
+            const float keep1 = hi16 ? tsum[3] : tsum[1];
+            const float send0 = hi16 ? tsum[0] : tsum[2];
+            const float send1 = hi16 ? tsum[1] : tsum[3];
+            const float u0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 16);
+            const float u1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
+            const float tot = (hi8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, hi8 ? u0 : u1, 8);
+            const int i = yy - ch;
+            if (gv && px_ok && i >= 0 && i < KS) gv[(long)i * plane] = tot;
+        };
+
+        mbar_wait(&bars[1], parity);
+        static_for<0, BP - 1>([&](auto YY) {
+            constexpr int yy = decltype(YY)::value;
+            float tsum[BP];
+            vh_row_v3<KS, CG, 0, yy + 1>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+            finish_row(yy, tsum);
+        });
+#pragma unroll
+        for (int q = 0; q < Cfg::NCHUNK; ++q) {
+            const int lo = max(BP - 1, q * Cfg::CH_TAPS);
+            const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
+            if (q > 0) mbar_wait(&bars[1 + q], parity);
+#pragma unroll 1
+            for (int yy = lo; yy < hi; ++yy) {
+                float tsum[BP];
+                vh_row_v3<KS, CG, 0, BP>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+                finish_row(yy, tsum);
+            }
+        }
+        static_for<0, BP - 1>([&](auto E) {
+            constexpr int yy = KS + decltype(E)::value;
+            float tsum[BP];
+            vh_row_v3<KS, CG, decltype(E)::value + 1, BP>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+            finish_row(yy, tsum);
+        });
+        parity ^= 1;
+
+        if (p.ghor && px_ok) {
+            float *gh = p.ghor + ((long)b * KS * Ho + y0) * Wo + px;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const int j = ch + 4 * jj;
+                if (j < KS) {
+#pragma unroll
+                    for (int r = 0; r < BP; ++r) gh[(long)j * plane + (long)r * Wo] = a[r][jj];
+                }
+            }
+        }
+        __syncthreads();  // slab and halo are free for the next tile
+    }
+}
+
+}  // namespace tai

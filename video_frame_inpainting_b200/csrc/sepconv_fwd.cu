@@ -25,34 +25,11 @@
 //     tai.py:105 / twi.py:105 in its epilogue.
 //
 // Algorithmic work per output element: 2*ks*ks flop (the ks extra vertical FMAs are not counted).
-#include <type_traits>
-
 #include "common.cuh"
+#include "sepconv_common.cuh"
+#include "sepconv_fwd_v3.cuh"
 
 namespace tai {
-
-constexpr int FP = 8;   // output rows per thread
-constexpr int FNX = 8;  // output columns per warp
-
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F &&f)
-{
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
-struct FwdParams {
-    const float *in[2];   // [B,C,Hi,Wi] (PAD: [B,C,Ho,Wo])
-    const float *ver[2];  // [B,ks,Ho,Wo]
-    const float *hor[2];
-    float *out[2];        // per-stream result (DUAL: dot1/dot2, may be null)
-    float *blend;         // DUAL only
-    float a, b;
-    int B, C, Ho, Wo, ks;
-    int ntx, nty;
-};
 
 // One input row of the sweep for output rows [RLO, RHI) of this thread.
 template <int J, int CG, int RLO, int RHI>
@@ -280,6 +257,50 @@ static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
     return check_launch("sepconv_fwd_kernel");
 }
 
+// Persistent TMA-fed kernel (sepconv_fwd_v3.cuh).  Returns +1 when this shape cannot use it (the kernel
+// maps are not TMA-describable: row pitch or base not 16 B aligned) so that the caller falls back.
+template <int KS, int CG, bool PAD, bool DUAL>
+static int launch_fwd_v3(const FwdParams &p0, cudaStream_t st)
+{
+    using Cfg = FwdV3Cfg<KS>;
+    FwdParams p = p0;
+    FwdV3Maps maps;
+    for (int s = 0; s < (DUAL ? 2 : 1); ++s) {
+        if (!make_kernel_map_tmap(&maps.h[s], p.hor[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+            !make_kernel_map_tmap(&maps.v[s], p.ver[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
+            return 1;
+    }
+    if (!DUAL) {
+        maps.h[1] = maps.h[0];
+        maps.v[1] = maps.v[0];
+    }
+    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
+    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
+    auto kern = sepconv_fwd_v3_kernel<KS, CG, PAD, DUAL>;
+    const size_t smem = Cfg::smem_bytes(CG);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    long ctas = (long)p.B * p.nty * p.ntx;
+    const long resident = (long)sm_count() * ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    return check_launch("sepconv_fwd_v3_kernel");
+}
+
+template <int KS, bool PAD, bool DUAL>
+static int launch_fwd_v3_c(const FwdParams &p, cudaStream_t st)
+{
+    return (p.C % 3 == 0) ? launch_fwd_v3<KS, 3, PAD, DUAL>(p, st) : launch_fwd_v3<KS, 1, PAD, DUAL>(p, st);
+}
+
 template <bool PAD, bool DUAL>
 static int launch_fwd(const FwdParams &p, cudaStream_t st)
 {
@@ -291,6 +312,17 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
         const long grid = (n + block - 1) / block;
         sepconv_fwd_simple_kernel<PAD, DUAL><<<(unsigned)(grid < 1 ? 1 : grid), block, 0, st>>>(p);
         return check_launch("sepconv_fwd_simple_kernel");
+    }
+    if (p.Ho >= FP) {
+        int rc = 1;
+        switch (ks) {  // the kernel sizes of BASELINE.json's sweep; 51 is the only one the models use
+            case 51: rc = launch_fwd_v3_c<51, PAD, DUAL>(p, st); break;
+            case 37: rc = launch_fwd_v3_c<37, PAD, DUAL>(p, st); break;
+            case 25: rc = launch_fwd_v3_c<25, PAD, DUAL>(p, st); break;
+            case 13: rc = launch_fwd_v3_c<13, PAD, DUAL>(p, st); break;
+            default: break;
+        }
+        if (rc <= 0) return rc;
     }
     const int j = ceil_div(ks, 4);
     const bool c3 = (p.C % 3 == 0);
