@@ -9,6 +9,7 @@
 // lane layout of the forward kernel; gI is a separate gather kernel.
 #include "common.cuh"
 #include "sepconv_bwd_vh_v3.cuh"
+#include "sepconv_bwd_i_v3.cuh"
 
 namespace tai {
 
@@ -405,9 +406,57 @@ static int launch_vh(const BwdParams &p, cudaStream_t st)
     return TAI_ERR_UNSUPPORTED;
 }
 
+// Persistent TMA-fed scatter kernel for gI (sepconv_bwd_i_v3.cuh); +1 = not TMA-describable, fall back.
+template <int KS>
+static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
+{
+    using Cfg = GiV3Cfg<KS>;
+    BwdParams p = p0;
+    GiV3Maps maps;
+    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+        !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
+        return 1;
+    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
+    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
+    auto kern = sepconv_bwd_i_v3_kernel<KS>;
+    const size_t smem = Cfg::smem_bytes();
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    const size_t gi_bytes = sizeof(float) * (size_t)p.B * p.C * (p.Ho + KS - 1) * (p.Wo + KS - 1);
+    cudaError_t e = cudaMemsetAsync(p.gin, 0, gi_bytes, st);  // the kernel accumulates with red.global
+    if (e != cudaSuccess) {
+        set_error("sepconv_bwd_i_v3: memset: %s", cudaGetErrorString(e));
+        return TAI_ERR_CUDA;
+    }
+    long ctas = (long)p.B * p.nty * p.ntx;
+    const long resident = (long)sm_count() * ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    return check_launch("sepconv_bwd_i_v3_kernel");
+}
+
 static int launch_gi(const BwdParams &p, cudaStream_t st)
 {
     const int Hi = p.Ho + p.ks - 1, Wi = p.Wo + p.ks - 1;
+    {
+        int rc = 1;
+        switch (p.ks) {
+            case 51: rc = launch_gi_v3<51>(p, st); break;
+            case 37: rc = launch_gi_v3<37>(p, st); break;
+            case 25: rc = launch_gi_v3<25>(p, st); break;
+            case 13: rc = launch_gi_v3<13>(p, st); break;
+            default: break;
+        }
+        if (rc <= 0) return rc;
+    }
     if ((p.C == 1 || p.C == 3) && p.B <= 65535 && ceil_div(Hi, GP) <= 65535) {
         dim3 grid(ceil_div(Wi, 128), ceil_div(Hi, GP), p.B);
         if (p.C == 1)

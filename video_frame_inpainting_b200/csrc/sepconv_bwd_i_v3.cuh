@@ -1,0 +1,214 @@
+// Gradient of the separable convolution w.r.t. its (padded) input, for sm_100a
+// (persistent, TMA-fed, scatter form; compile-time ks).
+//
+//   gI[b,c,Y+i,X+j] += gO[b,c,Y,X] * V[b,i,Y,X] * H[b,j,Y,X]       for every source pixel (Y,X), tap (i,j)
+//
+// which is kernel.cu:120-162 read from the source side: the reference's bounds test
+// X<0 || Y<0 || Y>=Ho || X>=Wo (kernel.cu:150) selects exactly the (source, tap) pairs that exist, so
+// looping over existing sources and all taps visits the same set of products.
+//
+// The reference gathers: one thread per gI element, 3 loads per FMA, V and H re-read ks*ks times.
+// Here each source pixel's kernels are read ONCE (same TMA slab scheme as the forward kernel) and the
+// sweep is the forward sweep transposed:
+//   * a warp owns 8 source columns x 8 source rows; lane = (cx = lane&7, ch = lane>>3) keeps the
+//     horizontal taps j == ch (mod 4) of its 8 source pixels in registers;
+//   * for destination row yy (relative to the tile), source row r contributes through vertical tap yy-r:
+//         t[j] = sum_r (V_{yy-r}(r) * gO_c(r)) * H_j(r)          8 FMAs per tap, V from the slab
+//     is this lane's contribution to destination column cx + j of that row;
+//   * the 4 x 13 values of a pixel column group are staged in shared memory and summed along the
+//     anti-diagonals cx + j = const (8 terms) by the warp itself: 58 destination columns per warp-row;
+//   * each warp keeps a private 58 x 58 destination window; after the sweep the CTA merges its four
+//     windows (they overlap by 50 columns) and adds the 58 x 82 result into gI with red.global
+//     (neighbouring tiles overlap by ks-1 rows/columns, so gI is zeroed by the launcher first).
+#pragma once
+
+#include "common.cuh"
+#include "sepconv_common.cuh"
+#include "sepconv_bwd_vh_v3.cuh"  // BwdParams
+#include "tma.cuh"
+
+namespace tai {
+
+template <int KS>
+struct GiV3Cfg {
+    static constexpr int J = (KS + 3) / 4;
+    static constexpr int WX = 4;
+    static constexpr int NT = 32 * WX;
+    static constexpr int TILE_W = WX * FNX, TILE_H = FP;
+    static constexpr int NCHUNK = 3;
+    static constexpr int CH_TAPS = (KS + NCHUNK - 1) / NCHUNK;
+    static constexpr int VROW = TILE_H * TILE_W;
+    static constexpr int SLAB_FLOATS = NCHUNK * CH_TAPS * VROW;
+    static constexpr int DROWS = TILE_H + KS - 1;    // destination rows per tile
+    static constexpr int WCOLS = FNX + KS - 1;       // destination columns per warp
+    static constexpr int DCOLS = TILE_W + KS - 1;    // destination columns per CTA
+    static constexpr int WIN_FLOATS = DROWS * WCOLS;
+    static constexpr int TS_PITCH = FNX + 1;
+    static constexpr int TS_FLOATS = KS * TS_PITCH;
+    static constexpr int NBAR = 1 + NCHUNK;
+    static constexpr size_t smem_bytes() { return (size_t)(SLAB_FLOATS + WX * (WIN_FLOATS + TS_FLOATS)) * 4 + 8 * NBAR; }
+};
+
+struct GiV3Maps {
+    CUtensorMap h;  // box {32, 8, KS, 1}
+    CUtensorMap v;  // box {32, 8, CH_TAPS, 1}
+};
+
+// One destination row: source rows [RLO, RHI) of this thread reach it (0 <= yy - r < KS).
+template <int KS, int RLO, int RHI>
+__device__ __forceinline__ void gi_row_v3(const float *__restrict__ vrow, const float (&h)[FP][(KS + 3) / 4],
+                                          const float (&go)[FP], float *__restrict__ ts, float *__restrict__ wrow,
+                                          int cx, int ch, int lane)
+{
+    using Cfg = GiV3Cfg<KS>;
+    constexpr int J = Cfg::J;
+    float vg[FP];
+#pragma unroll
+    for (int r = RLO; r < RHI; ++r) vg[r] = vrow[r * (Cfg::TILE_W - Cfg::VROW)] * go[r];  // tap yy-r of source row r
+    float t[J];
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj) t[jj] = vg[RLO] * h[RLO][jj];
+#pragma unroll
+    for (int r = RLO + 1; r < RHI; ++r)
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) t[jj] = fmaf(vg[r], h[r][jj], t[jj]);
+    // stage: ts[j][cx]
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj)
+        if (ch + 4 * jj < KS) ts[(ch + 4 * jj) * Cfg::TS_PITCH + cx] = t[jj];
+    __syncwarp();
+    // anti-diagonal sums: destination column d receives ts[d - c][c], c = 0..7
+    {
+        const int d0 = lane, d1 = lane + 32;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < FNX; ++c) {
+            const int j0 = d0 - c, j1 = d1 - c;
+            if (j0 >= 0 && j0 < KS) s0 += ts[j0 * Cfg::TS_PITCH + c];
+            if (j1 < KS && d1 < Cfg::WCOLS) s1 += ts[j1 * Cfg::TS_PITCH + c];
+        }
+        if (d0 < Cfg::WCOLS) wrow[d0] = s0;
+        if (d1 < Cfg::WCOLS) wrow[d1] = s1;
+    }
+    __syncwarp();
+}
+
+template <int KS>
+__global__ void __launch_bounds__(128, 2)
+sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p)
+{
+    using Cfg = GiV3Cfg<KS>;
+    constexpr int J = Cfg::J, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
+    static_assert(Cfg::WCOLS <= 64, "two destination columns per lane");
+    extern __shared__ __align__(128) float smem[];
+    float *slab = smem;
+    float *win = smem + Cfg::SLAB_FLOATS;                       // [4 warps][DROWS][WCOLS]
+    float *tsb = win + Cfg::WX * Cfg::WIN_FLOATS;               // [4 warps][KS][TS_PITCH]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tsb + Cfg::WX * Cfg::TS_FLOATS);
+
+    const int Ho = p.Ho, Wo = p.Wo;
+    const int Hi = Ho + KS - 1, Wi = Wo + KS - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cx = lane & 7, ch = lane >> 3;
+    const int ntiles = p.B * p.nty * p.ntx;
+    float *ts = tsb + warp * Cfg::TS_FLOATS;
+    float *mywin = win + warp * Cfg::WIN_FLOATS;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.ntx;
+        t /= p.ntx;
+        const int ty = t % p.nty;
+        const int b = t / p.nty;
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H;  // NOT shifted: a scatter must not visit a source twice
+        const int px = x0 + warp * FNX + cx;
+
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
+            tma_load_4d(slab, &maps.h, &bars[0], x0, y0, 0, b);  // out-of-range rows / columns arrive as zeros
+        }
+        mbar_wait(&bars[0], parity);
+        float h[FP][J];
+        {
+            const float *hs = slab + ch * Cfg::VROW + warp * FNX + cx;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj)
+#pragma unroll
+                for (int r = 0; r < FP; ++r)
+                    h[r][jj] = (ch + 4 * jj < KS) ? hs[(4 * jj) * Cfg::VROW + r * TILE_W] : 0.f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+#pragma unroll
+            for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                mbar_expect_tx(&bars[1 + q], Cfg::CH_TAPS * Cfg::VROW * 4);
+                tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v, &bars[1 + q], x0, y0, q * Cfg::CH_TAPS, b);
+            }
+            if (tile + (int)gridDim.x < ntiles) {
+                int n = tile + gridDim.x;
+                const int nx0 = (n % p.ntx) * TILE_W;
+                n /= p.ntx;
+                const int ny0 = (n % p.nty) * TILE_H, nb = n / p.nty;
+                tma_prefetch_l2_4d(&maps.h, nx0, ny0, 0, nb);
+#pragma unroll
+                for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
+            }
+        }
+        const float *vrow = slab + warp * FNX + cx;
+
+        for (int c = 0; c < p.C; ++c) {
+            float go[FP];
+#pragma unroll
+            for (int r = 0; r < FP; ++r)
+                go[r] = (px < Wo && y0 + r < Ho) ? __ldg(p.gout + ((long)(b * p.C + c) * Ho + y0 + r) * Wo + px) : 0.f;
+
+            if (c == 0) mbar_wait(&bars[1], parity);
+            static_for<0, FP - 1>([&](auto YY) {
+                constexpr int yy = decltype(YY)::value;
+                gi_row_v3<KS, 0, yy + 1>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);
+            });
+#pragma unroll
+            for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                const int lo = max(FP - 1, q * Cfg::CH_TAPS);
+                const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
+                if (q > 0 && c == 0) mbar_wait(&bars[1 + q], parity);
+#pragma unroll 1
+                for (int yy = lo; yy < hi; ++yy)
+                    gi_row_v3<KS, 0, FP>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);
+            }
+            static_for<0, FP - 1>([&](auto E) {
+                constexpr int yy = KS + decltype(E)::value;
+                gi_row_v3<KS, decltype(E)::value + 1, FP>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx,
+                                                         ch, lane);
+            });
+            __syncthreads();  // all four windows are complete
+
+            // ---- merge the four warp windows and add the tile's destination window into gI ----
+            float *gdst = p.gin + ((long)(b * p.C + c) * Hi + y0) * Wi + x0;
+            for (int idx = threadIdx.x; idx < Cfg::DROWS * Cfg::DCOLS; idx += Cfg::NT) {
+                const int yy = idx / Cfg::DCOLS, D = idx - yy * Cfg::DCOLS;
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < Cfg::WX; ++w) {
+                    const int dc = D - w * FNX;
+                    if (dc >= 0 && dc < Cfg::WCOLS) sum += win[w * Cfg::WIN_FLOATS + yy * Cfg::WCOLS + dc];
+                }
+                if (y0 + yy < Hi && x0 + D < Wi) atomicAdd(gdst + (long)yy * Wi + D, sum);
+            }
+            __syncthreads();  // windows are free for the next channel / tile
+        }
+        parity ^= 1;
+    }
+}
+
+}  // namespace tai
