@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native TAI / bi-TAI hot path (contract: see the task statement, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Default workload = BASELINE.json configs[1]: the KTH bi-TAI TRAINING STEP (model_key TAI_gray, c_dim 1,
+128x128, K = F = T = 5, batch 32 per GPU; generator + spectral-norm discriminator, losses and Adam as in
+the reference's TAITrainingEnvironment), on synthetic U(-1,1) clips with xavier-normal weights.  One
+"step" = forward + loss + backward + both optimiser updates.  Data-parallel over clips, weak scaling
+(32 clips per GPU), gradients all-reduced over NCCL.  The line printed by rank 0 carries:
+
+  value      frames/s (= N * B * T * K / time) with the batch already resident in HBM
+  e2e        the same metric through the public API with HOST (pinned) batches: H2D copies of the three
+             clip tensors and a D2H read of the losses inside the timed region, every step
+  roofline   the costliest kernel of THIS library inside the timed region, timed with CUDA events on its
+             own stream (tai_b200_timing_*): algorithmic flop / measured time against the FP32 FMA peak
+  cpu_baseline   the CPU port of the reference step (oracle/reference_model.py) on a bounded sample
+
+``--impl reference`` times that CPU port alone (the reference has no CPU path and cannot be imported under
+Python 3 / torch 2 -- DESIGN.md), on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bi-TAI inpainted frames/sec (KTH training step: fwd + bwd + Adam, generator and discriminator)"
+UNIT = "frames/s"
+
+WORKLOADS = {
+    # name: model_key, c_dim, H, W, K, T, F, batch per GPU, training?
+    "kth_train_b32": ("TAI_gray", 1, 128, 128, 5, 5, 5, 32, True),
+    "kth_infer_b1": ("TAI_gray", 1, 128, 128, 5, 5, 5, 1, False),
+    "ucf_infer_b8": ("TAI_color", 3, 240, 320, 5, 3, 5, 8, False),
+    "slomo_infer_b8": ("SloMoFillInModel_color", 3, 256, 320, 2, 3, 2, 8, False),
+}
+TRAIN_HP = dict(alpha=1.0, beta=0.02, lr=1e-4, beta1=0.5, df_dim=64, Ip=3, disc_window_size=3)  # options.py:72-99
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kth_train_b32", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 in the cuDNN convolutions (reported in config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        clocks, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                clocks.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        clocks.sort()
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx,
+                "samples": len(clocks), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_step_factory(workload, spatial=None):
+    import torch
+    from oracle.reference_model import CpuTAITrainingStep, to_cpu_reference
+    from video_frame_inpainting_b200.models.create_model import create_model
+    from video_frame_inpainting_b200.util.util import weights_init
+    key, c, H, W, K, T, F_, _, training = WORKLOADS[workload]
+    if spatial:
+        H, W = spatial
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    clip = torch.rand(1, K + T + F_, c, H, W, generator=g) * 2 - 1
+    pre, mid, fol = clip[:, :K].contiguous(), clip[:, K:K + T].contiguous(), clip[:, K + T:].contiguous()
+    if training:
+        st = CpuTAITrainingStep(create_model(key), (H, W), c, K, T, F_, alpha=TRAIN_HP["alpha"], beta=TRAIN_HP["beta"],
+                                lr=TRAIN_HP["lr"], beta1=TRAIN_HP["beta1"], df_dim=TRAIN_HP["df_dim"],
+                                Ip=TRAIN_HP["Ip"], disc_t=TRAIN_HP["disc_window_size"])
+        fn = lambda: st.step(pre, fol, mid)
+    else:
+        model = create_model(key)
+        model.apply(weights_init)
+        model = to_cpu_reference(model).eval()
+
+        def fn():
+            with torch.no_grad():
+                return model(T, pre, fol)
+    frames = T
+    sample = "%s: 1 step on 1 clip (batch 1 of the %dx%d workload, %d middle frames), FP32, torch CPU convs + C port of " \
+             "the reference kernels" % ("training" if training else "inference", H, W, T)
+    return fn, frames, sample
+
+
+def run_reference(args):
+    """--impl reference: the CPU port, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    fn, frames, sample = cpu_reference_step_factory(args.workload)
+    t0 = time.time()
+    fn()
+    first = time.time() - t0
+    spatial = None
+    if first * (args.steps + max(0, args.warmup - 1)) > 420.0:  # keep the whole run within a few minutes
+        spatial = (64, 64)
+        fn, frames, sample = cpu_reference_step_factory(args.workload, spatial)
+        sample += " [cropped to 64x64: the full-size step took %.1f s]" % first
+        fn()
+    for _ in range(max(0, args.warmup - 1)):
+        fn()
+    t0 = time.time()
+    for _ in range(args.steps):
+        fn()
+    dt = time.time() - t0
+    value = frames * args.steps / dt
+    cores = torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "device": "host CPU", "note": "reference has no CPU path; this is the "
+                   "CPU port of its training step (oracle/reference_model.py)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from video_frame_inpainting_b200 import _lib
+    from video_frame_inpainting_b200.environments.environments import (BaseVideoFillInEnvironment,
+                                                                      TAITrainingEnvironment)
+    from video_frame_inpainting_b200.models.create_model import create_model
+    from video_frame_inpainting_b200.parallel import init_distributed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    rank, local_rank, world = init_distributed()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = True
+    _lib.load()  # fail loudly here if the CUDA library is missing
+
+    key, c, H, W, K, T, F_, B, training = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    torch.manual_seed(0)  # same weights on every rank
+    model = create_model(key)
+    if training:
+        env = TAITrainingEnvironment(model, "/tmp/tai_b200_ckpt", "bench", (H, W), c, TRAIN_HP["alpha"],
+                                     TRAIN_HP["beta"], TRAIN_HP["lr"], TRAIN_HP["beta1"], TRAIN_HP["df_dim"],
+                                     TRAIN_HP["Ip"], TRAIN_HP["disc_window_size"], K, T, F_, (0, 0))
+        env.train()
+    else:
+        env = BaseVideoFillInEnvironment(model, "/tmp/tai_b200_ckpt", "bench", (0, 0))
+        env.eval()
+    env.K, env.T, env.F = K, T, F_
+
+    g = torch.Generator().manual_seed(1000 + rank)  # different clips per rank
+    host = torch.rand(B, K + T + F_, c, H, W, generator=g) * 2 - 1
+    h_pre = host[:, :K].contiguous().pin_memory()
+    h_mid = host[:, K:K + T].contiguous().pin_memory()
+    h_fol = host[:, K + T:].contiguous().pin_memory()
+    d_pre, d_mid, d_fol = h_pre.to(dev), h_mid.to(dev), h_fol.to(dev)
+
+    def step_resident():
+        if training:
+            env.preceding_frames, env.following_frames, env.gt_middle_frames = d_pre, d_fol, d_mid
+            env.forward_train()
+            env.optimize_parameters()
+        else:
+            env.preceding_frames, env.following_frames = d_pre, d_fol
+            env.forward_test()
+
+    def step_e2e():
+        if training:
+            env.set_train_inputs(h_pre, h_fol, h_mid)          # H2D from pinned memory
+            env.forward_train()
+            env.optimize_parameters()
+            return env.get_current_errors()                     # D2H of the loss scalars
+        env.set_test_inputs(h_pre, h_fol)
+        env.forward_test()
+        return float(env.gen_output['pred'].abs().mean())      # D2H of a result metric
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    _lib.timing_enable(True)
+    ms = timed(step_resident, args.steps)
+    kernel_times = _lib.timing_report()
+    _lib.timing_enable(False)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    step_e2e()  # warm the pinned-copy path
+    ms_e2e = timed(step_e2e, args.steps)
+
+    frames = world * B * T * args.steps
+    value = frames / (ms * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    h2d = (h_pre.numel() + h_fol.numel() + (h_mid.numel() if training else 0)) * 4
+    d2h = (10 if training else 1) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the costliest kernel of this library inside the timed region ----
+    peaks = measured_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fma_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s, nominal at the max SM clock
+    total_kernel_ms = sum(k["ms"] for k in kernel_times) or 1.0
+    kernel_times.sort(key=lambda k: -k["ms"])
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {})
+    roofline, per_kernel = None, []
+    for k in kernel_times:
+        avg_s = k["ms"] * 1e-3 / max(1, k["launches"])
+        entry = {"kernel": k["name"], "launches_per_step": k["launches"] / args.steps,
+                 "avg_us": avg_s * 1e6, "share_of_library_time": k["ms"] / total_kernel_ms,
+                 "share_of_step": k["ms"] / ms,
+                 "tflops": k["flops"] / max(1, k["launches"]) / avg_s / 1e12 if k["flops"] else 0.0,
+                 "gbs": k["bytes"] / max(1, k["launches"]) / avg_s / 1e9}
+        per_kernel.append(entry)
+    if per_kernel:
+        top = per_kernel[0]
+        compute_bound = top["tflops"] > 0
+        if compute_bound:
+            roofline = {"kernel": top["kernel"], "bound": "fp32_fma", "achieved": top["tflops"], "peak": fma_peak,
+                        "unit": "TFLOP/s", "frac": top["tflops"] / fma_peak,
+                        "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz, %s); not a tensor-core kernel"
+                                       % (sms, peaks["sm_max_mhz"], peaks["source"]),
+                        "hbm": {"achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": top["gbs"] / peaks["hbm_gbs"], "peak_source": peaks["source"]},
+                        "traffic": traffic.get(top["kernel"])}
+        else:
+            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": top["gbs"] / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                        "traffic": traffic.get(top["kernel"])}
+        roofline["avg_launch_us"] = top["avg_us"]
+        roofline["share_of_step"] = top["share_of_step"]
+        roofline["kernels"] = per_kernel
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        fn, cframes, sample = cpu_reference_step_factory(args.workload)
+        t0 = time.time()
+        fn()
+        dt = time.time() - t0
+        cpu_baseline = {"value": cframes / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": sample + "; single un-warmed step, %.1f s" % dt}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model_key": key, "clips_per_gpu": B, "global_clips": B * world,
+                   "frame": [c, H, W], "K": K, "T": T, "F": F_, "training": training, "ks": 51,
+                   "conv_math": "tf32" if args.tf32 else "fp32 (cudnn.allow_tf32=False)",
+                   "parallelism": "dp%d (clips sharded, NCCL all-reduce of gradients only)" % world,
+                   "l2": "per-step working set (activations, 4 x 107 MB kernel maps per middle frame) >> 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

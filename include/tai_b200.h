@@ -39,6 +39,13 @@ const char *tai_b200_last_error(void);
  * used by bench.py for its "gpu_launches" claim). */
 long long tai_b200_launch_count(void);
 
+/* Measurement support for bench.py: when enabled every kernel launch of this library is bracketed by
+ * CUDA events on its own stream; the report is a JSON array of
+ * {"name","launches","ms","flops","bytes"} (ms = summed event time, flops/bytes = the ALGORITHMIC work
+ * the launcher attributes to those launches).  Enabling clears earlier records. */
+int tai_b200_timing_enable(int on);
+int tai_b200_timing_report(char *buf, int buflen);
+
 /* ------------------------------------------------------------------------------------------
  * Per-pixel separable local convolution.
  *

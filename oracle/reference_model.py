@@ -1,0 +1,158 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference MODEL on the TAI path.
+
+The reference has no CPU implementation (its operator raises NotImplementedError on CPU tensors,
+SeparableConvolution.py:48-49; options.py:61 asserts a GPU) and cannot be imported under Python 3 /
+torch 2.  The CPU baseline that stands in for it is
+therefore a port: the same module tree as the product (so the convolution stack is identical and runs
+on torch's CPU kernels), with every hot-path operator replaced by the reference's own formulation:
+
+* separable convolution  -> the literal FP32 C port of kernel.cu:19-162 (oracle/sepconv_oracle.c),
+  called once per stream after an explicit ReplicationPad2d, followed by the blend as three
+  elementwise ops (tai.py:229-236, 105);
+* ConvLSTM gates          -> the chunk / sigmoid / tanh / cat chain of mcnet.py:287-293;
+* FlowWarper               -> host meshgrid + F.grid_sample with the torch-0.3.1 mapping (slomo.py:265-286).
+
+Used by bench.py (``cpu_baseline`` and ``--impl reference``) and by tests as an end-to-end checker of
+the GPU model.  Never imported by the product package.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+from video_frame_inpainting_b200.discriminators.SNDiscriminator import SNDiscriminator
+from video_frame_inpainting_b200.losses.losses import GDL
+from video_frame_inpainting_b200.models.mcnet.mcnet import ConvLstmCell
+from video_frame_inpainting_b200.models.slomo.slomo import FlowWarper, SloMo
+from video_frame_inpainting_b200.models.tai.tai import TAI
+from video_frame_inpainting_b200.util.util import inverse_transform, weights_init
+
+
+class CpuSeparableConvolution(torch.autograd.Function):
+    """SeparableConvolution.py:6-92 with the kernels replaced by their C port (FP32, reference loop order)."""
+
+    @staticmethod
+    def forward(ctx, input, vertical, horizontal, ks=51):
+        ctx.save_for_backward(input, vertical, horizontal)
+        ctx.constant = ks
+        out = O.sepconv_forward(input.numpy(), vertical.numpy(), horizontal.numpy(), ks, dtype=np.float32)
+        return torch.from_numpy(out)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, vertical, horizontal = ctx.saved_tensors
+        ks = ctx.constant
+        go = grad_output.contiguous().numpy()
+        gi = O.sepconv_grad_input(go, vertical.numpy(), horizontal.numpy(), ks, dtype=np.float32)
+        gv = O.sepconv_grad_vertical(go, input.numpy(), horizontal.numpy(), ks, dtype=np.float32)
+        gh = O.sepconv_grad_horizontal(go, input.numpy(), vertical.numpy(), ks, dtype=np.float32)
+        return torch.from_numpy(gi), torch.from_numpy(gv), torch.from_numpy(gh), None
+
+
+class CpuConvLstmCell(ConvLstmCell):
+    def gates(self, conv_output, state):
+        c, _ = torch.chunk(state, 2, dim=1)
+        i, j, f, o = torch.chunk(conv_output, 4, dim=1)
+        new_c = c * torch.sigmoid(f + self.forget_bias) + torch.sigmoid(i) * torch.tanh(j)
+        new_h = torch.tanh(new_c) * torch.sigmoid(o)
+        return torch.cat((new_c, new_h), dim=1)
+
+
+class CpuTAIMixin(object):
+    """Reference formulation of the filter-and-blend tail for TAI and its TWI subclass."""
+
+    def filter_and_blend(self, variableInput1, variableInput2, variableDyn1, variableDyn2, variableCont1,
+                         variableCont2, variableRes, ratio=0, a=0.5, b=0.5):
+        v1, h1, v2, h2 = self.kernel_maps(variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio)
+        apply = CpuSeparableConvolution.apply
+        dot1 = apply(self.modulePad(variableInput1).contiguous(), v1.contiguous(), h1.contiguous(), self.ks)
+        dot2 = apply(self.modulePad(variableInput2).contiguous(), v2.contiguous(), h2.contiguous(), self.ks)
+        return a * dot1 + b * dot2, dot1, dot2
+
+
+class CpuFlowWarper(FlowWarper):
+    def forward(self, img, uv):
+        H, W = int(img.shape[-2]), int(img.shape[-1])
+        gx, gy = np.meshgrid(np.arange(0, W), np.arange(0, H))
+        X = torch.Tensor(gx).unsqueeze(0) + uv[:, 0]
+        Y = torch.Tensor(gy).unsqueeze(0) + uv[:, 1]
+        grid = torch.stack((2 * (X / W - 0.5), 2 * (Y / H - 0.5)), dim=3)
+        return F.grid_sample(img, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
+
+
+class CpuSloMo(SloMo):
+    """Always the composed formulation of slomo.py:311-340 (no fused kernels)."""
+
+    def intermediate_flows_and_warps(self, I0, I1, F_0_1, F_1_0, t, differentiable):
+        return SloMo.intermediate_flows_and_warps(self, I0, I1, F_0_1, F_1_0, t, True)
+
+    def refine_and_blend(self, I0, I1, F_t_0, F_t_1, delta_F_t_0, delta_F_t_1, V_t_0, t, differentiable):
+        return SloMo.refine_and_blend(self, I0, I1, F_t_0, F_t_1, delta_F_t_0, delta_F_t_1, V_t_0, t, True)
+
+
+def to_cpu_reference(model):
+    """Re-class the hot-path modules of a (CPU-resident) product model to their reference formulations."""
+    for m in model.modules():
+        if type(m) is ConvLstmCell:
+            m.__class__ = CpuConvLstmCell
+        elif type(m) is FlowWarper:
+            m.__class__ = CpuFlowWarper
+        elif type(m) is SloMo:
+            m.__class__ = CpuSloMo
+        elif isinstance(m, TAI) and not isinstance(m, CpuTAIMixin):
+            m.__class__ = type('Cpu' + type(m).__name__, (CpuTAIMixin, type(m)), {})
+            m.separableConvolution = CpuSeparableConvolution.apply
+    return model
+
+
+class CpuTAITrainingStep(object):
+    """The TAI training step (environments.py:222-228, 326-379, 429-453) on CPU tensors: same losses,
+    optimisers and update order as video_frame_inpainting_b200.environments.TAITrainingEnvironment."""
+
+    def __init__(self, generator, image_size, c_dim, K, T, F_, alpha=1.0, beta=0.02, lr=1e-4, beta1=0.5, df_dim=64,
+                 Ip=3, disc_t=3):
+        self.generator = to_cpu_reference(generator)
+        self.generator.apply(weights_init)
+        self.discriminator = SNDiscriminator(image_size, c_dim, disc_t, df_dim, Ip)
+        self.discriminator.apply(weights_init)
+        self.K, self.T, self.F, self.disc_t = K, T, F_, disc_t
+        self.alpha, self.beta = alpha, beta
+        self.mse, self.gdl, self.bce = torch.nn.MSELoss(), GDL(), torch.nn.BCEWithLogitsLoss()
+        self.optimizer_G = torch.optim.Adam(self.generator.parameters(), lr=lr, betas=(beta1, 0.999))
+        self.optimizer_D = torch.optim.Adam(self.discriminator.parameters(), lr=lr, betas=(beta1, 0.999))
+
+    @staticmethod
+    def _tm01(frames):
+        _, _, c, H, W = frames.shape
+        return inverse_transform(frames.permute(1, 0, 2, 3, 4).contiguous().view(-1, c, H, W))
+
+    def _fake_labels(self):
+        n = self.K + self.T + self.F - self.disc_t + 1
+        ones_P, ones_F = max(0, self.K - self.disc_t + 1), max(0, self.F - self.disc_t + 1)
+        labels = torch.zeros(n)
+        labels[:ones_P] = 1
+        if ones_F > 0:
+            labels[n - ones_F:] = 1
+        return labels
+
+    def step(self, preceding, following, gt_middle):
+        out = self.generator(self.T, preceding, following)
+        gt = self._tm01(gt_middle)
+        self.optimizer_G.zero_grad()
+        loss = 0
+        for key in ('pred', 'pred_forward', 'pred_backward'):
+            x = self._tm01(out[key])
+            loss = loss + self.alpha * (self.mse(x, gt) + self.gdl(x, gt))
+        video = torch.cat([preceding, out['pred'], following], dim=1)
+        h = self.discriminator(video)
+        loss = loss + self.beta * self.bce(h, torch.ones_like(h))
+        loss.backward()
+        self.optimizer_G.step()
+        self.optimizer_D.zero_grad()
+        h = self.discriminator(video.detach())
+        labels = self._fake_labels().view(1, -1).expand(h.size(0), -1)
+        h_real = self.discriminator(torch.cat([preceding, gt_middle, following], dim=1))
+        loss_d = self.bce(h, labels) + self.bce(h_real, torch.ones_like(h_real))
+        loss_d.backward()
+        self.optimizer_D.step()
+        return float(loss.detach()), float(loss_d.detach())

@@ -1,0 +1,103 @@
+"""Host-side mirror of the reference model interface: registry keys, constructor signatures, state_dict
+names, output contracts.  The hot-path kernels need a GPU; on CPU the same module tree is exercised with
+the reference formulation of those operators (oracle/reference_model.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.reference_model import CpuTAITrainingStep, to_cpu_reference
+from video_frame_inpainting_b200.losses.losses import GDL
+from video_frame_inpainting_b200.models.create_model import create_model
+from video_frame_inpainting_b200.models.mcnet.mcnet import DecCnn
+from video_frame_inpainting_b200.models.slomo.slomo import SloMoFillInModel
+from video_frame_inpainting_b200.models.tai.tai import TAIFillInModel
+from video_frame_inpainting_b200.models.twi.twi import TimeWeightedInterpolationFillInModel
+from video_frame_inpainting_b200.util.util import weights_init
+
+
+def test_registry_and_parameter_counts():
+    """Parameter counts derived from the reference layer shapes: ~38.3 M for TAI_gray."""
+    gray = create_model('TAI_gray')
+    assert sum(p.numel() for p in gray.parameters()) == 38320861
+    keys = gray.state_dict().keys()
+    for expected in ('generator.motion_enc.dyn_conv1.0.weight', 'generator.conv_lstm_cell.conv.weight',
+                     'generator.dec_cnn.dec1.2.bias', 'merge_residual1.res.0.weight',
+                     'kernelnet.moduleConv.0.0.weight', 'kernelnet.moduleUpsample.3.1.weight',
+                     'kernelnet.moduleVertical1.7.weight', 'kernelnet.moduleHorizontal2.4.bias'):
+        assert expected in keys, expected
+    # num_block = 5: the ratio conv takes one extra channel (tai.py:335-340); num_block = 4 has no such block
+    assert gray.state_dict()['kernelnet.moduleUpsample.3.1.weight'].shape[1] == 65
+    color = create_model('TAI_color')
+    assert all(w.shape[1] % 2 == 0 for k, w in color.state_dict().items() if 'moduleUpsample' in k and k.endswith('1.weight'))
+    assert 'mcnet.motion_enc.dyn_conv1.0.weight' in create_model('TimeWeightedInterpolationFillInModel_gray').state_dict()
+    assert 'generator.compute_enc.enc1.0.weight' in create_model('SloMoFillInModel_color').state_dict()
+    with pytest.raises(RuntimeError):
+        create_model('OFFillInModel')
+
+
+def _tiny(cls=TAIFillInModel, c=1, num_block=5):
+    torch.manual_seed(0)
+    m = cls(8, c, 3, 5, num_block=num_block, kf_dim=4)
+    m.apply(weights_init)
+    return to_cpu_reference(m)
+
+
+@pytest.mark.parametrize("c,num_block", [(1, 5), (3, 4)])
+def test_forward_contract_and_time_conditioning(c, num_block):
+    m = _tiny(c=c, num_block=num_block)
+    B, K, T, F_ = 2, 3, 2, 4
+    pre, fol = torch.rand(B, K, c, 32, 32) * 2 - 1, torch.rand(B, F_, c, 32, 32) * 2 - 1
+    with torch.no_grad():
+        out = m(T, pre, fol)
+    assert set(out) == {'pred', 'pred_forward', 'pred_backward', 'interp_net_outputs_1', 'interp_net_outputs_2'}
+    for v in out.values():
+        assert v.shape == (B, T, c, 32, 32)
+    assert torch.allclose(out['pred'], 0.5 * out['interp_net_outputs_1'] + 0.5 * out['interp_net_outputs_2'], atol=1e-6)
+    # the ratio plane reaches the network only when num_block >= 5 (tai.py:213 with create_model.py:28,30)
+    args = [torch.randn(1, c, 32, 32), torch.randn(1, c, 32, 32)] + [torch.randn(1, 32, 4, 4) for _ in range(4)]
+    res = [torch.randn(1, 4, 32, 32), torch.randn(1, 8, 16, 16), torch.randn(1, 16, 8, 8)]
+    with torch.no_grad():
+        d_a = m.kernelnet(*args, res, ratio=0.25)[0]
+        d_b = m.kernelnet(*args, res, ratio=0.75)[0]
+    assert torch.equal(d_a, d_b) == (num_block < 5)
+
+
+def test_twi_blend_weights_and_slomo_order():
+    twi = _tiny(TimeWeightedInterpolationFillInModel)
+    assert twi.blend_weights(3) == [(0.75, 0.25, 0), (0.5, 0.5, 0), (0.25, 0.75, 0)]
+    with torch.no_grad():
+        out = twi(3, torch.rand(1, 2, 1, 32, 32), torch.rand(1, 2, 1, 32, 32))
+    assert torch.allclose(out['pred'][:, 0], 0.75 * out['interp_net_outputs_1'][:, 0] + 0.25 * out['interp_net_outputs_2'][:, 0], atol=1e-6)
+    torch.manual_seed(1)
+    s = SloMoFillInModel(4, 3)
+    s.apply(weights_init)
+    s = to_cpu_reference(s)
+    with torch.no_grad():
+        out = s(3, torch.rand(1, 2, 3, 64, 64) * 2 - 1, torch.rand(1, 2, 3, 64, 64) * 2 - 1)
+    assert out['pred'].shape == (1, 3, 3, 64, 64) and out['F_t_0_collector'].shape == (1, 3, 2, 64, 64)
+    # collectors are in REVERSE time order (slomo.py:332-340): entry 0 belongs to t = 3/4
+    t = 3 / 4
+    assert torch.allclose(out['F_t_0_collector'][:, 0], -(1 - t) * t * out['F_0_1'] + t * t * out['F_1_0'], atol=1e-6)
+
+
+def test_fixed_unpooling_and_gdl():
+    x = torch.arange(12.).view(1, 2, 2, 3)
+    up = DecCnn(1, 4).fixed_unpooling(x)
+    assert up.shape == (1, 2, 4, 6) and torch.equal(up[:, :, ::2, ::2], x) and up.sum() == x.sum()
+    a, b = torch.rand(2, 3, 5, 6), torch.rand(2, 3, 5, 6)
+    wa, wb = a[..., :, :-1] - a[..., :, 1:], b[..., :, :-1] - b[..., :, 1:]
+    ha, hb = a[..., 1:, :] - a[..., :-1, :], b[..., 1:, :] - b[..., :-1, :]
+    expect = ((wa - wb).abs()[..., 1:, :] + (ha - hb).abs()[..., :, 1:]).reshape(2, -1).mean()
+    assert torch.allclose(GDL()(a, b), expect)
+
+
+def test_cpu_reference_training_step_decreases_nothing_weird():
+    torch.manual_seed(0)
+    st = CpuTAITrainingStep(TAIFillInModel(8, 1, 3, 5, num_block=5, kf_dim=4), (32, 32), 1, 3, 2, 3, df_dim=8)
+    pre, fol, gt = (torch.rand(2, n, 1, 32, 32) * 2 - 1 for n in (3, 3, 2))
+    before = [p.detach().clone() for p in st.generator.parameters()]
+    lg, ld = st.step(pre, fol, gt)
+    assert np.isfinite(lg) and np.isfinite(ld)
+    changed = sum(int(not torch.equal(a, b)) for a, b in zip(before, st.generator.parameters()))
+    # merge_residual1 is computed but never consumed by the kernel net (tai.py:47,93 vs 221-226): no gradient
+    assert changed >= len(before) - 4

@@ -21,6 +21,8 @@ SIGNATURES = {
     "tai_b200_abi_version": (_c_i, []),
     "tai_b200_last_error": (ctypes.c_char_p, []),
     "tai_b200_launch_count": (ctypes.c_longlong, []),
+    "tai_b200_timing_enable": (_c_i, [_c_i]),
+    "tai_b200_timing_report": (_c_i, [ctypes.c_char_p, _c_i]),
     "SeparableConvolution_cuda_forward_b200": (_c_i, [_c_f] * 4 + [_c_i] * 5 + [_c_s]),
     "SeparableConvolution_cuda_backward_b200": (_c_i, [_c_f] * 7 + [_c_i] * 5 + [_c_s]),
     "tai_fused_forward_b200": (_c_i, [_c_f] * 9 + [_c_i] * 5 + [ctypes.c_float] * 2 + [_c_s]),
@@ -96,3 +98,16 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().tai_b200_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    """Bracket every kernel launch of the library with CUDA events (bench.py's roofline measurement)."""
+    call("tai_b200_timing_enable", 1 if on else 0)
+
+
+def timing_report():
+    """[{name, launches, ms, flops, bytes}] for the launches recorded since timing_enable(True)."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    call("tai_b200_timing_report", buf, len(buf))
+    return json.loads(buf.value.decode())

@@ -17,6 +17,16 @@ namespace tai {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-kernel timing (CUDA events on the launching stream), switched on by bench.py through
+// tai_b200_timing_enable().  `flops` / `bytes` are the ALGORITHMIC work of the launch.
+void timing_begin(const char *name, cudaStream_t st, double flops, double bytes);
+void timing_end(cudaStream_t st);
+struct TimingScope {
+    cudaStream_t st;
+    TimingScope(const char *name, cudaStream_t s, double flops, double bytes) : st(s) { timing_begin(name, s, flops, bytes); }
+    ~TimingScope() { timing_end(st); }
+};
+
 inline int check_launch(const char *what)
 {
     cudaError_t e = cudaGetLastError();

@@ -335,6 +335,7 @@ extern "C" int convlstm_gates_forward_b200(const float *conv_out, const float *s
     TAI_REQUIRE(fits_int31(4 * slab * B), TAI_ERR_TOO_LARGE, "convlstm_gates_forward_b200: tensor has >= 2^31 elements");
     const bool vec = (slab % 4 == 0) && ((((uintptr_t)conv_out | (uintptr_t)state | (uintptr_t)new_state) & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    TimingScope ts("gates_fwd", st, 0.0, 28.0 * B * slab);  // read i,j,f,o,c; write c',h'
     if (vec)
         gates_fwd_kernel<4><<<stream_grid(B * slab / 4, 256), 256, 0, st>>>(conv_out, state, new_state, B, slab, forget_bias);
     else
@@ -354,6 +355,7 @@ extern "C" int convlstm_gates_backward_b200(const float *conv_out, const float *
                      ((((uintptr_t)conv_out | (uintptr_t)state | (uintptr_t)g_new_state | (uintptr_t)g_conv_out |
                         (uintptr_t)g_state) & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    TimingScope ts("gates_bwd", st, 0.0, 52.0 * B * slab);  // read i,j,f,o,c,gc',gh'; write 4 + 2
     if (vec)
         gates_bwd_kernel<4><<<stream_grid(B * slab / 4, 256), 256, 0, st>>>(conv_out, state, g_new_state, g_conv_out, g_state, B, slab, forget_bias);
     else
@@ -374,6 +376,7 @@ extern "C" int flow_warp_forward_b200(const float *img, const float *uv, float *
     TAI_REQUIRE(img && uv && out, TAI_ERR_INVALID_ARGUMENT, "flow_warp_forward_b200: null pointer");
     int rc = warp_args_ok("flow_warp_forward_b200", B, C, H, W);
     if (rc) return rc;
+    TimingScope ts("warp_fwd", (cudaStream_t)stream, 0.0, 4.0 * (2.0 + 2.0 * C) * B * H * W);
     warp_fwd_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, uv, out, B, C, H, W);
     return check_launch("warp_fwd_kernel");
 }
@@ -389,6 +392,7 @@ extern "C" int flow_warp_backward_b200(const float *img, const float *uv, const 
         cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)B * C * H * W, st);
         TAI_REQUIRE(e == cudaSuccess, TAI_ERR_CUDA, "flow_warp_backward_b200: memset: %s", cudaGetErrorString(e));
     }
+    TimingScope ts("warp_bwd", st, 0.0, 4.0 * (4.0 + 3.0 * C) * B * H * W);
     warp_bwd_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, H, W);
     return check_launch("warp_bwd_kernel");
 }
@@ -405,6 +409,7 @@ extern "C" int slomo_flow_combine_warp_forward_b200(const float *i0, const float
     // Python-float (double) scalars of slomo.py:313-314, rounded to FP32 when they meet the tensor.
     const float c00 = (float)(-(1.0 - t) * t), c01 = (float)(t * t);
     const float c10 = (float)((1.0 - t) * (1.0 - t)), c11 = (float)(t * (1.0 - t));
+    TimingScope ts("slomo_combine_warp", (cudaStream_t)stream, 0.0, 4.0 * (8.0 + 4.0 * C) * B * H * W);
     slomo_combine_warp_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
         i0, i1, f01, f10, c00, c01, c10, c11, f_t0, f_t1, g0, g1, B, C, H, W);
     return check_launch("slomo_combine_warp_kernel");
@@ -419,6 +424,7 @@ extern "C" int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
                 "slomo_refine_blend_forward_b200: null pointer");
     int rc = warp_args_ok("slomo_refine_blend_forward_b200", B, C, H, W);
     if (rc) return rc;
+    TimingScope ts("slomo_refine_blend", (cudaStream_t)stream, 0.0, 4.0 * (9.0 + 3.0 * C) * B * H * W);
     slomo_refine_blend_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
         i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, (float)(1.0 - t), (float)t, out, B, C, H, W);
     return check_launch("slomo_refine_blend_kernel");

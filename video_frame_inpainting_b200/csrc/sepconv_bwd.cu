@@ -313,6 +313,24 @@ __global__ void fused_grad_mix_kernel(const float *gp, const float *g1, const fl
     }
 }
 
+// Algorithmic work of the backward launches.
+template <bool PAD>
+static void vh_work(const BwdParams &p, double *flops, double *bytes)
+{
+    const double px = (double)p.B * p.Ho * p.Wo;
+    const double in_el = PAD ? px * p.C : (double)p.B * p.C * (p.Ho + p.ks - 1) * (p.Wo + p.ks - 1);
+    const double outs = (p.gver ? 1.0 : 0.0) + (p.ghor ? 1.0 : 0.0);
+    *flops = 2.0 * 2.0 * px * p.C * p.ks * p.ks;
+    *bytes = 4.0 * (px * p.C + in_el + 2.0 * px * p.ks + outs * px * p.ks);
+}
+
+static void gi_work(const BwdParams &p, double *flops, double *bytes)
+{
+    const double px = (double)p.B * p.Ho * p.Wo;
+    *flops = 2.0 * px * p.C * p.ks * p.ks;
+    *bytes = 4.0 * (px * p.C + 2.0 * px * p.ks + (double)p.B * p.C * (p.Ho + p.ks - 1) * (p.Wo + p.ks - 1));
+}
+
 static inline unsigned ew_grid(long n, int block) { return (unsigned)((n + block - 1) / block > 148L * 16 ? 148 * 16 : (n + block - 1) / block < 1 ? 1 : (n + block - 1) / block); }
 
 template <int J, int CG, bool PAD>
@@ -331,7 +349,12 @@ static int launch_vh_tiled(const BwdParams &p0, cudaStream_t st)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
-    kern<<<(unsigned)((long)p.B * p.nty * p.ntx), 32 * WX * WY, smem, st>>>(p);
+    double fl, by;
+    vh_work<PAD>(p, &fl, &by);
+    {
+        TimingScope ts("sepconv_bwd_vh", st, fl, by);
+        kern<<<(unsigned)((long)p.B * p.nty * p.ntx), 32 * WX * WY, smem, st>>>(p);
+    }
     return check_launch("sepconv_bwd_vh_kernel");
 }
 
@@ -362,7 +385,12 @@ static int launch_vh_v3(const BwdParams &p0, cudaStream_t st)
     long ctas = (long)p.B * p.nty * p.ntx;
     const long resident = (long)sm_count() * ctas_per_sm;
     if (ctas > resident) ctas = resident;
-    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    double fl, by;
+    vh_work<PAD>(p, &fl, &by);
+    {
+        TimingScope ts("sepconv_bwd_vh", st, fl, by);
+        kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    }
     return check_launch("sepconv_bwd_vh_v3_kernel");
 }
 
@@ -379,7 +407,12 @@ static int launch_vh(const BwdParams &p, cudaStream_t st)
     const bool tiled = ks >= 4 && ks <= 64 && p.Ho >= BP && (p.C == 1 || p.C == 3);
     if (!tiled) {
         const long n = (long)p.B * ks * p.Ho * p.Wo;
-        sepconv_bwd_vh_simple_kernel<PAD><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
+        double fl, by;
+        vh_work<PAD>(p, &fl, &by);
+        {
+            TimingScope ts("sepconv_bwd_vh", st, fl, by);
+            sepconv_bwd_vh_simple_kernel<PAD><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
+        }
         return check_launch("sepconv_bwd_vh_simple_kernel");
     }
     {
@@ -439,7 +472,12 @@ static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
     long ctas = (long)p.B * p.nty * p.ntx;
     const long resident = (long)sm_count() * ctas_per_sm;
     if (ctas > resident) ctas = resident;
-    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    double fl, by;
+    gi_work(p, &fl, &by);
+    {
+        TimingScope ts("sepconv_bwd_i", st, fl, by);
+        kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    }
     return check_launch("sepconv_bwd_i_v3_kernel");
 }
 
@@ -459,14 +497,24 @@ static int launch_gi(const BwdParams &p, cudaStream_t st)
     }
     if ((p.C == 1 || p.C == 3) && p.B <= 65535 && ceil_div(Hi, GP) <= 65535) {
         dim3 grid(ceil_div(Wi, 128), ceil_div(Hi, GP), p.B);
-        if (p.C == 1)
-            sepconv_bwd_i_kernel<1><<<grid, 128, 0, st>>>(p);
-        else
-            sepconv_bwd_i_kernel<3><<<grid, 128, 0, st>>>(p);
+        double fl, by;
+        gi_work(p, &fl, &by);
+        {
+            TimingScope ts("sepconv_bwd_i", st, fl, by);
+            if (p.C == 1)
+                sepconv_bwd_i_kernel<1><<<grid, 128, 0, st>>>(p);
+            else
+                sepconv_bwd_i_kernel<3><<<grid, 128, 0, st>>>(p);
+        }
         return check_launch("sepconv_bwd_i_kernel");
     }
     const long n = (long)p.B * p.C * Hi * Wi;
-    sepconv_bwd_i_simple_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
+    double fl, by;
+    gi_work(p, &fl, &by);
+    {
+        TimingScope ts("sepconv_bwd_i", st, fl, by);
+        sepconv_bwd_i_simple_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
+    }
     return check_launch("sepconv_bwd_i_simple_kernel");
 }
 
@@ -525,7 +573,10 @@ extern "C" int tai_fused_backward_b200(const float *grad_pred, const float *grad
     cudaStream_t st = (cudaStream_t)stream;
     const long n = (long)B * C * H * W;
     float *gd1 = (float *)workspace, *gd2 = gd1 + n, *gpad = gd2 + n;
-    fused_grad_mix_kernel<<<ew_grid(n, 256), 256, 0, st>>>(grad_pred, grad_dot1, grad_dot2, gd1, gd2, a, b, n);
+    {
+        TimingScope ts("fused_grad_mix", st, 0.0, 4.0 * 5.0 * n);
+        fused_grad_mix_kernel<<<ew_grid(n, 256), 256, 0, st>>>(grad_pred, grad_dot1, grad_dot2, gd1, gd2, a, b, n);
+    }
     int rc = check_launch("fused_grad_mix_kernel");
     for (int s = 0; s < 2 && rc == TAI_OK; ++s) {
         BwdParams p{};
@@ -542,7 +593,10 @@ extern "C" int tai_fused_backward_b200(const float *grad_pred, const float *grad
         if (rc == TAI_OK && gdst) {
             rc = launch_gi(p, st);
             if (rc == TAI_OK) {
-                reppad_bwd_kernel<<<ew_grid(n, 256), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
+                {
+                    TimingScope ts("reppad_bwd", st, 0.0, 4.0 * ((double)B * C * (H + ks - 1) * (W + ks - 1) + n));
+                    reppad_bwd_kernel<<<ew_grid(n, 256), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
+                }
                 rc = check_launch("reppad_bwd_kernel");
             }
         }

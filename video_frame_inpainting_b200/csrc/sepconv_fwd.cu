@@ -236,6 +236,20 @@ __global__ void sepconv_fwd_simple_kernel(const FwdParams p)
     }
 }
 
+// Algorithmic work of one forward launch: 2*ks*ks flop per output element and
+// stream; every operand read once, every result written once.
+template <bool PAD, bool DUAL>
+static void fwd_work(const FwdParams &p, double *flops, double *bytes)
+{
+    const double ns = DUAL ? 2.0 : 1.0;
+    const double px = (double)p.B * p.Ho * p.Wo;
+    const double in_el = PAD ? px * p.C : (double)p.B * p.C * (p.Ho + p.ks - 1) * (p.Wo + p.ks - 1);
+    double outs = 1.0;
+    if (DUAL) outs = 1.0 + (p.out[0] ? 1.0 : 0.0) + (p.out[1] ? 1.0 : 0.0);
+    *flops = ns * 2.0 * px * p.C * p.ks * p.ks;
+    *bytes = 4.0 * (ns * in_el + ns * 2.0 * px * p.ks + outs * px * p.C);
+}
+
 template <int J, int CG, bool PAD, bool DUAL>
 static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
 {
@@ -253,7 +267,12 @@ static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
         attr_done = true;
     }
     const long blocks = (long)p.B * p.nty * p.ntx;
-    kern<<<(unsigned)blocks, 32 * WX * WY, smem, st>>>(p);
+    double fl, by;
+    fwd_work<PAD, DUAL>(p, &fl, &by);
+    {
+        TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
+        kern<<<(unsigned)blocks, 32 * WX * WY, smem, st>>>(p);
+    }
     return check_launch("sepconv_fwd_kernel");
 }
 
@@ -291,7 +310,12 @@ static int launch_fwd_v3(const FwdParams &p0, cudaStream_t st)
     long ctas = (long)p.B * p.nty * p.ntx;
     const long resident = (long)sm_count() * ctas_per_sm;
     if (ctas > resident) ctas = resident;
-    kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    double fl, by;
+    fwd_work<PAD, DUAL>(p, &fl, &by);
+    {
+        TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
+        kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    }
     return check_launch("sepconv_fwd_v3_kernel");
 }
 
@@ -310,7 +334,12 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
         const long n = (long)p.B * p.C * p.Ho * p.Wo;
         const int block = 128;
         const long grid = (n + block - 1) / block;
-        sepconv_fwd_simple_kernel<PAD, DUAL><<<(unsigned)(grid < 1 ? 1 : grid), block, 0, st>>>(p);
+        double fl, by;
+        fwd_work<PAD, DUAL>(p, &fl, &by);
+        {
+            TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
+            sepconv_fwd_simple_kernel<PAD, DUAL><<<(unsigned)(grid < 1 ? 1 : grid), block, 0, st>>>(p);
+        }
         return check_launch("sepconv_fwd_simple_kernel");
     }
     if (p.Ho >= FP) {

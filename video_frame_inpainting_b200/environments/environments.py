@@ -1,0 +1,260 @@
+"""Training / evaluation step of the TAI path (callers of the hot path).
+
+Restates ``src/environments/environments.py`` of the reference for torch 2 -- the classes on the TAI path
+only (``BaseVideoFillInEnvironment`` :64-119, ``BaseTrainingEnvironment`` :122-259,
+``L2GDLDiscTrainingEnvironment`` :262-397, ``TAITrainingEnvironment`` :415-485) with the same method
+names, loss composition and checkpoint dictionary.  Differences, all on the host side:
+
+* ``Variable`` / ``volatile`` / ``.cuda(async=True)`` (a SyntaxError on Python 3, environments.py:94)
+  become plain tensors, ``torch.no_grad()`` and ``.cuda(non_blocking=True)``;
+* gradients live in one flat buffer per network and are all-reduced bucket by bucket while backward is
+  still running (``parallel.FlatGradAllReducer``) when the process group has more than one rank -- the
+  reference is single-GPU;
+* nothing here launches a custom kernel directly: the kernels are reached through
+  ``generator(T, preceding, following)``.
+"""
+import os
+
+import numpy as np
+import torch
+
+from ..discriminators.SNDiscriminator import SNDiscriminator
+from ..losses.losses import GDL
+from ..parallel import FlatGradAllReducer, broadcast_module
+from ..util.util import inverse_transform, move_to_devices, weights_init
+
+
+def create_training_environment(fill_in_model, c_dim, checkpoints_dir, name, max_K, max_T, max_F, image_size, alpha,
+                                beta, lr, beta1, df_dim, Ip, disc_window_size, padding_size=(0, 0)):
+    """Factory (environments.py:24-52), TAI-path models only.  Resumes from model_latest.ckpt if present."""
+    env = TAITrainingEnvironment(fill_in_model, checkpoints_dir, name, image_size, c_dim, alpha, beta, lr, beta1,
+                                 df_dim, Ip, disc_window_size, max_K, max_T, max_F, padding_size)
+    if os.path.isfile(os.path.join(checkpoints_dir, name, 'model_latest.ckpt')):
+        env.load('model_latest.ckpt')
+    return env
+
+
+def create_eval_environment(fill_in_model, checkpoints_dir, name, snapshot_file_name, padding_size=(0, 0)):
+    env = BaseVideoFillInEnvironment(fill_in_model, checkpoints_dir, name, padding_size)
+    if snapshot_file_name is not None:
+        env.load(snapshot_file_name)
+    return env
+
+
+class BaseVideoFillInEnvironment(object):
+    """Owns the generator; ``set_test_inputs`` / ``forward_test``   (environments.py:64-119)."""
+
+    def __init__(self, video_fill_in_model, checkpoints_dir, name, padding_size):
+        self.save_dir = os.path.join(checkpoints_dir, name)
+        self.padding_size = padding_size
+        self.generator = move_to_devices(video_fill_in_model)
+        self.generator.apply(weights_init)
+        self.K = self.T = self.F = None
+
+    def set_test_inputs(self, preceding_frames, following_frames):
+        self.preceding_frames = preceding_frames.contiguous().cuda(non_blocking=True)
+        self.following_frames = following_frames.contiguous().cuda(non_blocking=True)
+
+    def set_gt_middle_frames_test(self, gt_middle_frames):
+        self.gt_middle_frames = gt_middle_frames.contiguous().cuda(non_blocking=True)
+
+    def forward_test(self):
+        with torch.no_grad():
+            self.gen_output = self.generator(self.T, self.preceding_frames, self.following_frames)
+
+    def load(self, snapshot_file_name):
+        save_path = os.path.join(self.save_dir, snapshot_file_name)
+        if not os.path.isfile(save_path):
+            raise RuntimeError('Failed to find snapshot at path %s' % save_path)
+        snapshot = torch.load(save_path, map_location='cuda')
+        self.generator.load_state_dict(snapshot['generator'])
+        return snapshot
+
+    def eval(self):
+        self.generator.eval()
+
+
+class BaseTrainingEnvironment(BaseVideoFillInEnvironment):
+    def __init__(self, fill_in_model, checkpoints_dir, name, lr, beta1, max_K, max_T, max_F, padding_size):
+        super(BaseTrainingEnvironment, self).__init__(fill_in_model, checkpoints_dir, name, padding_size)
+        self.start_update = 0
+        self.total_updates = 0
+        self.start_sum_avg_psnr_err = 0
+        self.start_sum_avg_ssim_err = 0
+        self.max_K, self.max_T, self.max_F = max_K, max_T, max_F
+        broadcast_module(self.generator)
+        self.reducer_G = FlatGradAllReducer(self.generator)
+        self.optimizer_G = torch.optim.Adam(self.generator.parameters(), lr=lr, betas=(beta1, 0.999))
+
+    def sample_KTF(self, allow_random_sampling):
+        if allow_random_sampling:
+            return (np.random.randint(1, self.max_K + 1), np.random.randint(1, self.max_T + 1),
+                    np.random.randint(1, self.max_F + 1))
+        return self.max_K, self.max_T, self.max_F
+
+    def set_train_inputs(self, preceding_frames, following_frames, gt_middle_frames):
+        self.preceding_frames = preceding_frames.contiguous().cuda(non_blocking=True)
+        self.following_frames = following_frames.contiguous().cuda(non_blocking=True)
+        self.gt_middle_frames = gt_middle_frames.contiguous().cuda(non_blocking=True)
+
+    def forward_train(self):
+        self.gen_output = self.generator(self.T, self.preceding_frames, self.following_frames)
+
+    def get_current_state_dict(self, total_updates, sum_avg_psnr_err, sum_avg_ssim_err):
+        return {
+            'updates': total_updates,
+            'sum_avg_psnr_err': sum_avg_psnr_err,
+            'sum_avg_ssim_err': sum_avg_ssim_err,
+            'generator': self.generator.state_dict(),
+            'optimizer_G': self.optimizer_G.state_dict(),
+        }
+
+    def load(self, snapshot_file_name):
+        snapshot = super(BaseTrainingEnvironment, self).load(snapshot_file_name)
+        self.start_update = snapshot['updates']
+        self.start_sum_avg_psnr_err = snapshot['sum_avg_psnr_err']
+        self.start_sum_avg_ssim_err = snapshot['sum_avg_ssim_err']
+        self.optimizer_G.load_state_dict(snapshot['optimizer_G'])
+        return snapshot
+
+    def save(self, snapshot_file_name, total_updates, sum_avg_psnr_err, sum_avg_ssim_err):
+        os.makedirs(self.save_dir, exist_ok=True)
+        torch.save(self.get_current_state_dict(total_updates, sum_avg_psnr_err, sum_avg_ssim_err),
+                   os.path.join(self.save_dir, snapshot_file_name))
+
+    def optimize_parameters(self):
+        """One generator update (environments.py:222-228)."""
+        self.reducer_G.zero_grad()
+        self.compute_loss_G()
+        self.reducer_G.arm()
+        self.loss_G.backward()
+        self.reducer_G.finish()
+        self.optimizer_G.step()
+
+    def compute_loss_G(self):
+        self.loss_G = torch.zeros(1, device='cuda')
+
+    def get_current_errors(self):
+        return {'G_loss': float(self.loss_G)}
+
+    def train(self):
+        self.generator.train()
+
+
+class L2GDLDiscTrainingEnvironment(BaseTrainingEnvironment):
+    """L2 + GDL + adversarial loss; spectral-norm discriminator with its own Adam   (environments.py:262-397)."""
+
+    def __init__(self, fill_in_model, checkpoints_dir, name, image_size, c_dim, alpha, beta, lr, beta1, df_dim, Ip,
+                 disc_t, max_K, max_T, max_F, padding_size):
+        super(L2GDLDiscTrainingEnvironment, self).__init__(fill_in_model, checkpoints_dir, name, lr, beta1, max_K,
+                                                           max_T, max_F, padding_size)
+        self.loss_Lp = torch.nn.MSELoss()
+        self.loss_gdl = GDL()
+        self.loss_d = torch.nn.BCEWithLogitsLoss()
+        self.alpha, self.beta = alpha, beta
+        self.disc_t = disc_t
+        discriminator = SNDiscriminator((image_size[0] + padding_size[0], image_size[1] + padding_size[1]), c_dim,
+                                        disc_t, df_dim, Ip)
+        self.discriminator = move_to_devices(discriminator)
+        self.discriminator.apply(weights_init)
+        broadcast_module(self.discriminator)
+        self.reducer_D = FlatGradAllReducer(self.discriminator)
+        self.optimizer_D = torch.optim.Adam(self.discriminator.parameters(), lr=lr, betas=(beta1, 0.999))
+
+    def get_current_state_dict(self, total_updates, sum_avg_psnr_err, sum_avg_ssim_err):
+        state = super(L2GDLDiscTrainingEnvironment, self).get_current_state_dict(total_updates, sum_avg_psnr_err,
+                                                                                 sum_avg_ssim_err)
+        state['discriminator'] = self.discriminator.state_dict()
+        state['optimizer_D'] = self.optimizer_D.state_dict()
+        return state
+
+    def load(self, snapshot_file_name):
+        snapshot = super(L2GDLDiscTrainingEnvironment, self).load(snapshot_file_name)
+        self.discriminator.load_state_dict(snapshot['discriminator'])
+        self.optimizer_D.load_state_dict(snapshot['optimizer_D'])
+        return snapshot
+
+    def create_fake_labels(self):
+        """Windows that contain only real (preceding / following) frames are labelled 1 (environments.py:308-323)."""
+        n = self.K + self.T + self.F - self.disc_t + 1
+        ones_P = max(0, self.K - self.disc_t + 1)
+        ones_F = max(0, self.F - self.disc_t + 1)
+        labels = torch.zeros(n)
+        labels[:ones_P] = 1
+        if ones_F > 0:
+            labels[n - ones_F:] = 1
+        return labels
+
+    def _video(self, middle):
+        return torch.cat([self.preceding_frames, middle, self.following_frames], dim=1)
+
+    def compute_loss_D(self):
+        h = self.discriminator(self._video(self.gen_output['pred']).detach())
+        fake_labels = self.create_fake_labels().to(h.device).view(1, -1).expand(h.size(0), -1)
+        self.loss_d_fake = self.loss_d(h, fake_labels)
+        h_ = self.discriminator(self._video(self.gt_middle_frames).detach())
+        self.loss_d_real = self.loss_d(h_, torch.ones_like(h_))
+        self.loss_D = self.loss_d_fake + self.loss_d_real
+
+    def optimize_parameters(self):
+        super(L2GDLDiscTrainingEnvironment, self).optimize_parameters()
+        self.reducer_D.zero_grad()
+        self.compute_loss_D()
+        self.reducer_D.arm()
+        self.loss_D.backward()
+        self.reducer_D.finish()
+        self.optimizer_D.step()
+
+    @staticmethod
+    def _time_major01(frames):
+        """[B,T,C,H,W] in [-1,1] -> [T*B,C,H,W] in [0,1], same-time frames grouped (environments.py:363-369)."""
+        _, _, c, H, W = frames.shape
+        return inverse_transform(frames.permute(1, 0, 2, 3, 4).contiguous().view(-1, c, H, W))
+
+    def compute_loss_G(self):
+        super(L2GDLDiscTrainingEnvironment, self).compute_loss_G()
+        gt = self._time_major01(self.gt_middle_frames)
+        outputs = self._time_major01(self.gen_output['pred'])
+        self.Lp = self.loss_Lp(outputs, gt)
+        self.gdl = self.loss_gdl(outputs, gt)
+        h = self.discriminator(self._video(self.gen_output['pred']))
+        self.L_GAN = self.loss_d(h, torch.ones_like(h))
+        self.loss_G = self.loss_G + self.alpha * (self.Lp + self.gdl) + self.beta * self.L_GAN
+
+    def get_current_errors(self):
+        errors = super(L2GDLDiscTrainingEnvironment, self).get_current_errors()
+        errors.update(G_Lp=float(self.Lp), G_gdl=float(self.gdl), D_real=float(self.loss_d_real),
+                      D_fake=float(self.loss_d_fake), G_GAN=float(self.L_GAN))
+        return errors
+
+    def train(self):
+        super(L2GDLDiscTrainingEnvironment, self).train()
+        self.discriminator.train()
+
+
+class TAITrainingEnvironment(L2GDLDiscTrainingEnvironment):
+    """Adds the reconstruction losses of the two intermediate predictions   (environments.py:415-485)."""
+
+    def sample_KTF(self, allow_random_sampling):
+        if allow_random_sampling:
+            return (np.random.randint(2, self.max_K + 1), np.random.randint(1, self.max_T + 1),
+                    np.random.randint(2, self.max_F + 1))
+        return self.max_K, self.max_T, self.max_F
+
+    def compute_loss_G(self):
+        super(TAITrainingEnvironment, self).compute_loss_G()
+        gt = self._time_major01(self.gt_middle_frames)
+        fwd = self._time_major01(self.gen_output['pred_forward'])
+        bwd = self._time_major01(self.gen_output['pred_backward'])
+        self.Lp_forward = self.loss_Lp(fwd, gt)
+        self.Lp_backward = self.loss_Lp(bwd, gt)
+        self.gdl_forward = self.loss_gdl(fwd, gt)
+        self.gdl_backward = self.loss_gdl(bwd, gt)
+        self.loss_G = self.loss_G + self.alpha * (self.Lp_forward + self.Lp_backward + self.gdl_forward
+                                                  + self.gdl_backward)
+
+    def get_current_errors(self):
+        errors = super(TAITrainingEnvironment, self).get_current_errors()
+        errors.update(G_Lp_forward=float(self.Lp_forward), G_gdl_forward=float(self.gdl_forward),
+                      G_Lp_backward=float(self.Lp_backward), G_gdl_backward=float(self.gdl_backward))
+        return errors

@@ -1,0 +1,203 @@
+"""bi-TAI: bidirectional MC-Net + TAI kernel network, with the filter-and-blend tail on sm_100a kernels.
+
+Host-side mirror of the reference's ``src/models/tai/tai.py``: same classes, constructor signatures,
+attribute names (``generator``, ``merge_residual{1,2,3}``, ``kernelnet``, ``moduleConv`` ...) and output
+dict.  What changes on the hot path:
+
+* reference, per middle frame: 2 x ReplicationPad2d -> 2 x SeparableConvolution -> 0.5*Dot1 + 0.5*Dot2
+  (tai.py:229-236, 105): 2 pad kernels, 2 naive sepconv kernels, 3 elementwise kernels;
+* here: ONE launch of ``tai_fused_forward_b200`` (pad folded into the halo load, both streams filtered,
+  blend in the epilogue, Dot1/Dot2 still emitted because they are part of the output dict, tai.py:117-118).
+  ``TAI.forward`` keeps its reference contract (returns Dot1, Dot2) and ``TAI.filter_and_blend`` is the
+  fused entry that ``TAIFillInModel.forward`` uses.
+
+torch-0.3.1 semantics pinned here: ``nn.Upsample(mode='bilinear')`` interpolated with the
+align-corners mapping, so every bilinear upsample is ``align_corners=True``; ``xrange`` / py2 ``/`` are
+``range`` / ``//``.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn import functional as F
+
+from ... import ops
+from ...separable_convolution.SeparableConvolution import SeparableConvolution
+from ..mcnet.mcnet import MCNet, Residual, gray_difference_frames
+
+
+def _up2():
+    return nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+
+
+class TAIFillInModel(nn.Module):
+    """``forward(T, preceding_frames[B,K,C,H,W], following_frames[B,F,C,H,W])`` -> dict with keys
+    pred, pred_forward, pred_backward, interp_net_outputs_1, interp_net_outputs_2   (tai.py:14-120)."""
+
+    def __init__(self, gf_dim, c_dim, feature_size, ks, num_block=5, kf_dim=32, layers=3, forget_bias=1,
+                 activation=F.tanh, bias=True):
+        super(TAIFillInModel, self).__init__()
+        self.c_dim = c_dim
+        self.conv_lstm_state_size = 8 * gf_dim
+        self.generator = MCNet(gf_dim, c_dim, feature_size, forget_bias=forget_bias, activation=activation, bias=bias)
+        self.merge_residual3 = Residual(gf_dim * 8, kf_dim * 4)
+        self.merge_residual2 = Residual(gf_dim * 4, kf_dim * 2)
+        self.merge_residual1 = Residual(gf_dim * 2, kf_dim * 1)
+        self.kernelnet = TAI(gf_dim, ks, num_block, layers, kf_dim)
+
+    def blend_weights(self, T):
+        """(a_t, b_t) of pred_t = a_t*Dot1 + b_t*Dot2 and the time ratio fed to the kernel net.
+        bi-TAI: a = b = 0.5 (tai.py:105), ratio_t = 1 - w_t, w = linspace(0,1,T+2)[1:-1] (tai.py:90,99)."""
+        w = np.linspace(0, 1, num=T + 2).tolist()[1:-1]
+        return [(0.5, 0.5, 1 - w[t]) for t in range(T)]
+
+    def forward(self, T, preceding_frames, following_frames):
+        K = preceding_frames.size(1)
+        F_ = following_frames.size(1)
+        xt = preceding_frames[:, -1]
+        xt_F = following_frames[:, 0]
+        diff_in = gray_difference_frames(preceding_frames)
+        diff_in_F = gray_difference_frames(torch.flip(following_frames, dims=[1]))  # time-reversed (tai.py:71-74)
+
+        forward_pred, forward_dyn, forward_cont, forward_res = self.generator(K, T, diff_in, xt)
+        backward_pred, backward_dyn, backward_cont, backward_res = self.generator(F_, T, diff_in_F, xt_F)
+        backward_pred, backward_dyn = backward_pred[::-1], backward_dyn[::-1]
+        backward_cont, backward_res = backward_cont[::-1], backward_res[::-1]
+
+        combination, outputs_1, outputs_2 = [], [], []
+        for t, (a, b, ratio) in enumerate(self.blend_weights(T)):
+            merged_res = [self.merge_residual1(forward_res[t][0], backward_res[t][0]),
+                          self.merge_residual2(forward_res[t][1], backward_res[t][1]),
+                          self.merge_residual3(forward_res[t][2], backward_res[t][2])]
+            pred_t, dot1, dot2 = self.kernelnet.filter_and_blend(
+                forward_pred[t], backward_pred[t], forward_dyn[t], backward_dyn[t], forward_cont[t],
+                backward_cont[t], merged_res, ratio=ratio, a=a, b=b)
+            combination.append(pred_t)
+            outputs_1.append(dot1)
+            outputs_2.append(dot2)
+
+        return {
+            'pred': torch.stack(combination, dim=1),
+            'pred_forward': torch.stack(forward_pred, dim=1),
+            'pred_backward': torch.stack(backward_pred, dim=1),
+            'interp_net_outputs_1': torch.stack(outputs_1, dim=1),
+            'interp_net_outputs_2': torch.stack(outputs_2, dim=1),
+        }
+
+
+class TAI(nn.Module):
+    """Kernel network: encoder / decoder over [dyn1, dyn2, cont1, cont2] -> four 1-D kernel maps
+    V1, H1, V2, H2 [B, ks, H, W], applied to the two predictions   (tai.py:123-237)."""
+
+    RC_LOC = 4  # decoder block (1-based) that receives the time-ratio plane; TWI overrides it with -1
+
+    def __init__(self, gf_dim, ks, num_block, layers, kf_dim):
+        super(TAI, self).__init__()
+        assert layers >= 1, 'layers in per block should be no smaller than 1, but layers=[%d]' % layers
+        assert num_block >= 4, '# blocks should be no less than 3, but num_block=%d' % num_block
+        self.kf_dim = kf_dim
+        self.ks = ks
+        self.layers = layers
+        self.num_block = num_block
+        self.rc_loc = self.RC_LOC
+
+        moduleConv, modulePool = create_encoder_blocks(3, num_block, layers, gf_dim * 8 * 2, kf_dim)
+        self.moduleConv = nn.ModuleList(moduleConv)
+        self.modulePool = nn.ModuleList(modulePool)
+        moduleDeconv, moduleUpsample = create_decoder_blocks(num_block - 1, kf_dim, layers, self.rc_loc)
+        self.moduleDeconv = nn.ModuleList(moduleDeconv)
+        self.moduleUpsample = nn.ModuleList(moduleUpsample)
+
+        self.moduleVertical1 = create_1d_kernel_generator_block(layers, kf_dim, ks)
+        self.moduleVertical2 = create_1d_kernel_generator_block(layers, kf_dim, ks)
+        self.moduleHorizontal1 = create_1d_kernel_generator_block(layers, kf_dim, ks)
+        self.moduleHorizontal2 = create_1d_kernel_generator_block(layers, kf_dim, ks)
+
+        pad = int(math.floor(ks / 2.0))
+        self.modulePad = nn.ReplicationPad2d([pad, pad, pad, pad])
+        self.separableConvolution = SeparableConvolution.apply
+
+    def kernel_maps(self, variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio=0):
+        """Everything of tai.py:188-226,230-235 that produces V1, H1, V2, H2."""
+        nb = self.num_block
+        x = torch.cat([variableDyn1, variableDyn2, variableCont1, variableCont2], 1)
+        enc = []
+        for i in range(nb - 3):
+            enc.append(self.moduleConv[i](x))
+            x = self.modulePool[i](enc[-1])
+        for i in range(nb - 1):
+            x = self.moduleDeconv[i](x)
+            if i == self.rc_loc - 1:  # time-ratio plane; reachable only when num_block >= 5 (tai.py:213-217)
+                x = torch.cat([x, x.new_full((x.size(0), 1, x.size(2), x.size(3)), float(ratio))], dim=1)
+            x = self.moduleUpsample[i](x)
+            x = x + (enc[nb - 3 - i - 1] if i < nb - 3 else variableRes[nb - i - 1])
+        return (self.moduleVertical1(x), self.moduleHorizontal1(x), self.moduleVertical2(x), self.moduleHorizontal2(x))
+
+    def forward(self, variableInput1, variableInput2, variableDyn1, variableDyn2, variableCont1, variableCont2,
+                variableRes, ratio=0):
+        """Reference contract: returns (Dot1, Dot2), the two filtered predictions (tai.py:174-237), through
+        the reference-shaped operator ``SeparableConvolution.apply(pad(x), V, H, ks)``."""
+        v1, h1, v2, h2 = self.kernel_maps(variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio)
+        dot1 = self.separableConvolution(self.modulePad(variableInput1).contiguous(), v1, h1, self.ks)
+        dot2 = self.separableConvolution(self.modulePad(variableInput2).contiguous(), v2, h2, self.ks)
+        return dot1, dot2
+
+    def filter_and_blend(self, variableInput1, variableInput2, variableDyn1, variableDyn2, variableCont1,
+                         variableCont2, variableRes, ratio=0, a=0.5, b=0.5):
+        """Fused tail: (a*Dot1 + b*Dot2, Dot1, Dot2) in one kernel launch (pad + 2 x sepconv + blend)."""
+        v1, h1, v2, h2 = self.kernel_maps(variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio)
+        return ops.tai_blend_sepconv(variableInput1.contiguous(), variableInput2.contiguous(), v1.contiguous(),
+                                     h1.contiguous(), v2.contiguous(), h2.contiguous(), self.ks, a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# builders (tai.py:244-347); module indices inside each Sequential match the reference's
+# ------------------------------------------------------------------------------------------------
+
+def create_basic_conv_block(num_layers, num_in_channels, num_out_channels):
+    """num_layers x (3x3 conv, ReLU), resolution preserving   (tai.py:244-263)."""
+    seq = []
+    cin = num_in_channels
+    for _ in range(num_layers):
+        seq += [nn.Conv2d(cin, num_out_channels, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False)]
+        cin = num_out_channels
+    return nn.Sequential(*seq)
+
+
+def create_1d_kernel_generator_block(num_layers, kf_dim, ks):
+    """(num_layers-1) x conv(2kf->2kf)+ReLU, conv(2kf->ks)+ReLU, bilinear x2, conv(ks->ks); the output has
+    no normalisation and may be negative   (tai.py:266-286)."""
+    seq = []
+    for i in range(num_layers):
+        cout = ks if i == num_layers - 1 else kf_dim * 2
+        seq += [nn.Conv2d(kf_dim * 2, cout, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False)]
+    seq += [_up2(), nn.Conv2d(ks, ks, kernel_size=3, stride=1, padding=1)]
+    return nn.Sequential(*seq)
+
+
+def create_encoder_blocks(start_i, end_i, layers, if_dim, kf_dim):
+    """Blocks i = start_i..end_i-1 with kf_dim * 2**i channels, each followed by AvgPool2d(2) (tai.py:289-310)."""
+    convs, pools = [], []
+    cin = if_dim
+    for i in range(start_i, end_i):
+        cout = kf_dim * (2 ** i)
+        convs.append(create_basic_conv_block(layers, cin, cout))
+        pools.append(nn.AvgPool2d(kernel_size=2, stride=2))
+        cin = cout
+    return convs, pools
+
+
+def create_decoder_blocks(num_block, kf_dim, layers, rc_loc):
+    """Decoder block i: conv block, then bilinear x2 + conv + ReLU; block rc_loc-1 takes one extra input
+    channel (the time ratio)   (tai.py:313-347)."""
+    deconvs, upsamples = [], []
+    for i in range(num_block):
+        c_out = kf_dim * 2 ** (num_block - i)
+        c_in = c_out if i == 0 else kf_dim * 2 ** (num_block - i + 1)
+        deconvs.append(create_basic_conv_block(layers, c_in, c_out))
+        extra = 1 if i == rc_loc - 1 else 0
+        upsamples.append(nn.Sequential(_up2(),
+                                       nn.Conv2d(c_out + extra, c_out, kernel_size=3, stride=1, padding=1),
+                                       nn.ReLU(inplace=False)))
+    return deconvs, upsamples
