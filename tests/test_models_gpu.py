@@ -28,7 +28,7 @@ def test_bitai_forward_and_backward_match_cpu_reference(cuda, c, num_block, ks):
     gpu_model.apply(weights_init)
     cpu_model = to_cpu_reference(copy.deepcopy(gpu_model))
     gpu_model = gpu_model.cuda()
-    B, K, T, F_, H, W = 2, 3, 2, 3, 32, 48
+    B, K, T, F_, H, W = 2, 3, 2, 3, 32, 64
     pre, fol = torch.rand(B, K, c, H, W) * 2 - 1, torch.rand(B, F_, c, H, W) * 2 - 1
     out_g = gpu_model(T, pre.cuda(), fol.cuda())
     out_c = cpu_model(T, pre, fol)

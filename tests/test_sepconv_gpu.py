@@ -121,6 +121,9 @@ def test_replication_pad_index_bit_exact(cuda, H, W, p):
     (2, 3, 24, 40, 51, 0.75, 0.25),    # TWI blend (twi.py:105), w = 0.25
     (1, 3, 16, 36, 13, 1.0 / 3, 2.0 / 3),
     (1, 1, 5, 7, 5, 0.5, 0.5),         # fallback
+    (2, 1, 32, 64, 13, 0.5, 0.5),      # small ks: the 7 prologue rows span two TMA tap chunks
+    (1, 1, 16, 32, 25, 0.5, 0.5),
+    (1, 3, 24, 32, 37, 0.5, 0.5),
 ])
 def test_fused_pad_sepconv_blend(cuda, B, C, H, W, ks, a, b):
     from video_frame_inpainting_b200 import ops
@@ -142,7 +145,7 @@ def test_fused_pad_sepconv_blend(cuda, B, C, H, W, ks, a, b):
     assert np.array_equal(pred_only.cpu().numpy(), pred.cpu().numpy())
 
 
-@pytest.mark.parametrize("B,C,H,W,ks", [(1, 1, 16, 32, 51), (2, 3, 12, 36, 13), (1, 1, 5, 7, 5)])
+@pytest.mark.parametrize("B,C,H,W,ks", [(1, 1, 16, 32, 51), (2, 3, 12, 36, 13), (1, 1, 5, 7, 5), (2, 1, 32, 64, 13)])
 def test_fused_backward(cuda, B, C, H, W, ks):
     import torch
     from video_frame_inpainting_b200 import ops

@@ -172,7 +172,11 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
             for (int r = 0; r < FP; ++r)
                 go[r] = (px < Wo && y0 + r < Ho) ? __ldg(p.gout + ((long)(b * p.C + c) * Ho + y0 + r) * Wo + px) : 0.f;
 
-            if (c == 0) mbar_wait(&bars[1], parity);
+            constexpr int PRO_CHUNKS = (FP - 2) / Cfg::CH_TAPS + 1;  // chunks touched by the prologue rows
+            if (c == 0) {
+#pragma unroll
+                for (int q = 0; q < PRO_CHUNKS; ++q) mbar_wait(&bars[1 + q], parity);
+            }
             static_for<0, FP - 1>([&](auto YY) {
                 constexpr int yy = decltype(YY)::value;
                 gi_row_v3<KS, 0, yy + 1>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);
@@ -181,7 +185,7 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
             for (int q = 0; q < Cfg::NCHUNK; ++q) {
                 const int lo = max(FP - 1, q * Cfg::CH_TAPS);
                 const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
-                if (q > 0 && c == 0) mbar_wait(&bars[1 + q], parity);
+                if (q >= PRO_CHUNKS && c == 0) mbar_wait(&bars[1 + q], parity);
 #pragma unroll 1
                 for (int yy = lo; yy < hi; ++yy)
                     gi_row_v3<KS, 0, FP>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);

@@ -235,7 +235,9 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             if (gv && px_ok && i >= 0 && i < KS) gv[(long)i * plane] = tot;
         };
 
-        mbar_wait(&bars[1], parity);
+        constexpr int PRO_CHUNKS = (BP - 2) / Cfg::CH_TAPS + 1;  // chunks touched by the prologue rows
+#pragma unroll
+        for (int q = 0; q < PRO_CHUNKS; ++q) mbar_wait(&bars[1 + q], parity);
         static_for<0, BP - 1>([&](auto YY) {
             constexpr int yy = decltype(YY)::value;
             float tsum[BP];
@@ -246,7 +248,7 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
         for (int q = 0; q < Cfg::NCHUNK; ++q) {
             const int lo = max(BP - 1, q * Cfg::CH_TAPS);
             const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
-            if (q > 0) mbar_wait(&bars[1 + q], parity);
+            if (q >= PRO_CHUNKS) mbar_wait(&bars[1 + q], parity);
 #pragma unroll 1
             for (int yy = lo; yy < hi; ++yy) {
                 float tsum[BP];

@@ -239,7 +239,10 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                 const float *srow = is + warp * FNX + cx + ch;
                 const float *vrow = slab + warp * FNX + cx;  // tap 0, row 0
 
-                mbar_wait(&bars[1], parity);
+                // the prologue rows touch vertical taps 0..FP-2: wait for every chunk that holds one of them
+                constexpr int PRO_CHUNKS = (FP - 2) / Cfg::CH_TAPS + 1;
+#pragma unroll
+                for (int q = 0; q < PRO_CHUNKS; ++q) mbar_wait(&bars[1 + q], parity);
                 LAB_T(3);
                 // prologue: input rows 0..6 (output rows 0..yy are inside the window)
                 static_for<0, FP - 1>([&](auto YY) {
@@ -251,7 +254,7 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                 for (int q = 0; q < Cfg::NCHUNK; ++q) {
                     const int lo = max(FP - 1, q * Cfg::CH_TAPS);
                     const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
-                    if (q > 0) mbar_wait(&bars[1 + q], parity);
+                    if (q >= PRO_CHUNKS) mbar_wait(&bars[1 + q], parity);
 #pragma unroll 1
                     for (int yy = lo; yy < hi; ++yy)
                         fwd_row_v3<KS, CG, 0, FP>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, acc);

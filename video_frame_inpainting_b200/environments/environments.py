@@ -135,7 +135,7 @@ class BaseTrainingEnvironment(BaseVideoFillInEnvironment):
         self.loss_G = torch.zeros(1, device='cuda')
 
     def get_current_errors(self):
-        return {'G_loss': float(self.loss_G)}
+        return {'G_loss': float(self.loss_G.detach())}
 
     def train(self):
         self.generator.train()
@@ -223,8 +223,9 @@ class L2GDLDiscTrainingEnvironment(BaseTrainingEnvironment):
 
     def get_current_errors(self):
         errors = super(L2GDLDiscTrainingEnvironment, self).get_current_errors()
-        errors.update(G_Lp=float(self.Lp), G_gdl=float(self.gdl), D_real=float(self.loss_d_real),
-                      D_fake=float(self.loss_d_fake), G_GAN=float(self.L_GAN))
+        errors.update(G_Lp=float(self.Lp.detach()), G_gdl=float(self.gdl.detach()),
+                      D_real=float(self.loss_d_real.detach()), D_fake=float(self.loss_d_fake.detach()),
+                      G_GAN=float(self.L_GAN.detach()))
         return errors
 
     def train(self):
@@ -255,6 +256,6 @@ class TAITrainingEnvironment(L2GDLDiscTrainingEnvironment):
 
     def get_current_errors(self):
         errors = super(TAITrainingEnvironment, self).get_current_errors()
-        errors.update(G_Lp_forward=float(self.Lp_forward), G_gdl_forward=float(self.gdl_forward),
-                      G_Lp_backward=float(self.Lp_backward), G_gdl_backward=float(self.gdl_backward))
+        errors.update(G_Lp_forward=float(self.Lp_forward.detach()), G_gdl_forward=float(self.gdl_forward.detach()),
+                      G_Lp_backward=float(self.Lp_backward.detach()), G_gdl_backward=float(self.gdl_backward.detach()))
         return errors
