@@ -183,28 +183,24 @@ def run_reference(args):
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
 
-def run_b200(args):
+def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0):
+    """Model + environment + synthetic clips of a named workload on cuda:local_rank.
+    Returns (step_resident, step_e2e, info)."""
     import torch
-    import torch.distributed as dist
     from video_frame_inpainting_b200 import _lib
     from video_frame_inpainting_b200.environments.environments import (BaseVideoFillInEnvironment,
                                                                       TAITrainingEnvironment)
     from video_frame_inpainting_b200.models.create_model import create_model
-    from video_frame_inpainting_b200.parallel import init_distributed
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
-    rank, local_rank, world = init_distributed()
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     torch.backends.cudnn.benchmark = True
     _lib.load()  # fail loudly here if the CUDA library is missing
 
-    key, c, H, W, K, T, F_, B, training = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
+    key, c, H, W, K, T, F_, B, training = WORKLOADS[workload]
+    if batch:
+        B = batch
     torch.manual_seed(0)  # same weights on every rank
     model = create_model(key)
     if training:
@@ -243,6 +239,34 @@ def run_b200(args):
         env.forward_test()
         return float(env.gen_output['pred'].abs().mean())      # D2H of a result metric
 
+    h2d = (h_pre.numel() + h_fol.numel() + (h_mid.numel() if training else 0)) * 4
+    info = dict(key=key, c=c, H=H, W=W, K=K, T=T, F=F_, B=B, training=training, h2d=h2d,
+                d2h=(10 if training else 1) * 4, env=env)
+    return step_resident, step_e2e, info
+
+
+def make_step(workload, batch=0):
+    """(step, info) for tools/step_profile.py and other single-GPU harnesses."""
+    import torch
+    torch.cuda.set_device(0)
+    step, _, info = build_workload(workload, batch)
+    return step, info
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from video_frame_inpainting_b200 import _lib
+    from video_frame_inpainting_b200.parallel import init_distributed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    rank, local_rank, world = init_distributed()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    step_resident, step_e2e, info = build_workload(args.workload, args.batch, args.tf32, rank, local_rank)
+    key, c, H, W, K, T, F_, B, training = (info[k] for k in ("key", "c", "H", "W", "K", "T", "F", "B", "training"))
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -280,8 +304,7 @@ def run_b200(args):
     frames = world * B * T * args.steps
     value = frames / (ms * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
-    h2d = (h_pre.numel() + h_fol.numel() + (h_mid.numel() if training else 0)) * 4
-    d2h = (10 if training else 1) * 4
+    h2d, d2h = info["h2d"], info["d2h"]
 
     if rank != 0:
         if world > 1:

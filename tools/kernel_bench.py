@@ -36,6 +36,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="kth,ucf,small")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--no-probe", action="store_true")
     ap.add_argument("--ref", action="store_true", help="also time the reference kernels (oracle/_ref)")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
@@ -49,7 +51,7 @@ def main():
     U = lambda *s: torch.rand(*s, device=dev, generator=g) * 2 - 1
 
     # FFMA ceiling
-    for packed in (False, True):
+    for packed in (() if args.no_probe else (False, True)):
         grid, block, iters = 148 * 8, 256, 4096
         med, best = timeit(lambda: ops.ffma_probe(grid, block, iters, packed), iters=5)
         fl = 2.0 * 8 * iters * grid * block
@@ -82,7 +84,7 @@ def main():
         for k, (fn, fl, by) in runs.items():
             if args.only and k not in args.only.split(","):
                 continue
-            med, best = timeit(fn, iters=args.iters, flush=flush)
+            med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
             print(json.dumps({"case": name, "shape": [B, C, Ho, Wo, ks], "kernel": k, "ms_med": med * 1e3,
                               "ms_best": best * 1e3, "tflops": fl / med / 1e12, "frac_fma_peak": fl / med / PEAK_FMA,
                               "gbs": by / med / 1e9}), flush=True)

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "sepconv_common.cuh"
 #include "sepconv_fwd_v3.cuh"
+#include "sepconv_fwd_v5.cuh"
 
 namespace tai {
 
@@ -325,6 +326,52 @@ static int launch_fwd_v3_c(const FwdParams &p, cudaStream_t st)
     return (p.C % 3 == 0) ? launch_fwd_v3<KS, 3, PAD, DUAL>(p, st) : launch_fwd_v3<KS, 1, PAD, DUAL>(p, st);
 }
 
+
+// Persistent chunk-ring kernel (sepconv_fwd_v5.cuh).  Returns +1 when this shape cannot use it (the kernel
+// maps are not TMA-describable: row pitch or base not 16 B aligned) so that the caller falls back.
+template <int KS, int CG, bool PAD, bool DUAL>
+static int launch_fwd_v5(const FwdParams &p0, cudaStream_t st)
+{
+    using Cfg = FwdV5Cfg<KS>;
+    FwdParams p = p0;
+    FwdV5Maps maps;
+    for (int s = 0; s < (DUAL ? 2 : 1); ++s) {
+        if (!make_kernel_map_tmap(&maps.h[s], p.hor[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CT) ||
+            !make_kernel_map_tmap(&maps.v[s], p.ver[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CT))
+            return 1;
+    }
+    if (!DUAL) {
+        maps.h[1] = maps.h[0];
+        maps.v[1] = maps.v[0];
+    }
+    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
+    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
+    auto kern = sepconv_fwd_v5_kernel<KS, CG, PAD, DUAL>;
+    const size_t smem = Cfg::smem_bytes(CG);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    // one contiguous tile range per CTA, balanced per SM first (blockIdx % nsm shares an SM in practice)
+    const long ntiles = (long)p.B * p.nty * p.ntx;
+    const int nsm = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    int cps = (int)((ntiles + nsm - 1) / nsm);
+    if (cps > ctas_per_sm) cps = ctas_per_sm;
+    double fl, by;
+    fwd_work<PAD, DUAL>(p, &fl, &by);
+    {
+        TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
+        kern<<<(unsigned)(nsm * cps), Cfg::NT, smem, st>>>(maps, p, cps);
+    }
+    return check_launch("sepconv_fwd_v5_kernel");
+}
+
 template <bool PAD, bool DUAL>
 static int launch_fwd(const FwdParams &p, cudaStream_t st)
 {
@@ -344,9 +391,14 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
     }
     if (p.Ho >= FP) {
         int rc = 1;
+        // Two persistent TMA kernels; the choice per shape class is the measured one (profiles/r01_notes.md):
+        // v5 (chunk ring + halo row ring, one pass per prediction stream) wins where the halo is expensive --
+        // three colour channels and a large window (UCF, ks = 51: fused 0.62 ms vs 0.98 ms); v3 (whole-box slab,
+        // both streams per tile) wins for one channel and for small windows (KTH fused: 0.185 ms vs 0.224 ms).
+        const bool ring = (p.C % 3 == 0) && ks >= 37;
         switch (ks) {  // the kernel sizes of BASELINE.json's sweep; 51 is the only one the models use
-            case 51: rc = launch_fwd_v3_c<51, PAD, DUAL>(p, st); break;
-            case 37: rc = launch_fwd_v3_c<37, PAD, DUAL>(p, st); break;
+            case 51: rc = ring ? launch_fwd_v5<51, 3, PAD, DUAL>(p, st) : launch_fwd_v3_c<51, PAD, DUAL>(p, st); break;
+            case 37: rc = ring ? launch_fwd_v5<37, 3, PAD, DUAL>(p, st) : launch_fwd_v3_c<37, PAD, DUAL>(p, st); break;
             case 25: rc = launch_fwd_v3_c<25, PAD, DUAL>(p, st); break;
             case 13: rc = launch_fwd_v3_c<13, PAD, DUAL>(p, st); break;
             default: break;

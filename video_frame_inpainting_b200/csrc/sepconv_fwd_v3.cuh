@@ -80,13 +80,17 @@ __device__ __forceinline__ void fwd_row_v3(const float *__restrict__ srow, const
         float iv[J];
 #pragma unroll
         for (int jj = 0; jj < J; ++jj) iv[jj] = srow[c * CSTRIDE + 4 * jj];
+        // tap-outer order: the row sums are independent FMA chains that interleave (row-outer order makes ptxas
+        // emit one serial chain after the other: 4-cycle dependent issue with 3 warps per scheduler)
+        float s[FP];
 #pragma unroll
-        for (int r = RLO; r < RHI; ++r) {
-            float s = h[r][0] * iv[0];
+        for (int r = RLO; r < RHI; ++r) s[r] = h[r][0] * iv[0];
 #pragma unroll
-            for (int jj = 1; jj < J; ++jj) s = fmaf(h[r][jj], iv[jj], s);
-            acc[c][r] = fmaf(v[r], s, acc[c][r]);
-        }
+        for (int jj = 1; jj < J; ++jj)
+#pragma unroll
+            for (int r = RLO; r < RHI; ++r) s[r] = fmaf(h[r][jj], iv[jj], s[r]);
+#pragma unroll
+        for (int r = RLO; r < RHI; ++r) acc[c][r] = fmaf(v[r], s[r], acc[c][r]);
     }
 }
 
