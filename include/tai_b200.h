@@ -153,6 +153,24 @@ int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
                                     double t, float *out, int B, int C, int H, int W, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Decoder resampling.  N = B*C planes of H x W; results are 2H x 2W.
+ *
+ * Bilinear x2 upsample with the torch-0.3.1 mapping (today's align_corners=True):
+ * replaces nn.Upsample(scale_factor=2, mode='bilinear') of src/models/tai/tai.py:283,337,343 and
+ * src/models/slomo/slomo.py:113-149.  src = d*(in-1)/(out-1) in FP32, i0 = (int)src, i1 = i0 + (i0 < in-1).
+ * The backward entry is its adjoint, evaluated as a gather (no atomics, deterministic).
+ */
+int upsample_bilinear2x_forward_b200(const float *in, float *out, long long N, int H, int W, void *stream);
+int upsample_bilinear2x_backward_b200(const float *grad_out, float *grad_in, long long N, int H, int W, void *stream);
+
+/* Zero-insertion unpooling fused with the residual add of DecCnn:
+ * replaces  fixed_unpooling(x) + res   src/models/mcnet/mcnet.py:234-236 (the add), 240-256 (two cats,
+ * clone().zero_(), two permutes):  out[n,2y,2x] = x[n,y,x] + res[n,2y,2x], out = res elsewhere.
+ * x [N,H,W], res / out [N,2H,2W].  Adjoint: grad_res = grad_out (no kernel), grad_x[n,y,x] = grad_out[n,2y,2x]. */
+int unpool_add_forward_b200(const float *x, const float *res, float *out, long long N, int H, int W, void *stream);
+int unpool_backward_b200(const float *grad_out, float *grad_x, long long N, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helper: a pure FFMA loop, used by bench.py to report the on-box FP32 FMA
  * ceiling next to the nominal 148 x 128 x 2 x f_SM.  Writes one float per thread to `sink`
  * (gridDim*blockDim floats).  flops = 2 * 8 * iters * grid * block. */

@@ -406,6 +406,51 @@ def fixed_unpooling(x):
     return out
 
 
+def upsample_bilinear2x_taps(n_in):
+    """Integer taps and FP32 weights of the torch-0.3.1 bilinear x2 upsample along one axis (the library
+    computed src = d * ((in-1)/(out-1)) in FP32, i0 = (int)src, i1 = i0 + (i0 < in-1), lambda = src - i0).
+    Returns (i0, i1, w0, w1) for d = 0 .. 2*n_in-1; the integer arrays are compared bit-exactly."""
+    n_out = 2 * n_in
+    ratio = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(0)
+    d = np.arange(n_out, dtype=np.float32)
+    src = (ratio * d).astype(np.float32)
+    i0 = src.astype(np.int64)
+    i1 = i0 + (i0 < n_in - 1)
+    w1 = (src - i0.astype(np.float32)).astype(np.float32)
+    w0 = (np.float32(1) - w1).astype(np.float32)
+    return i0, i1, w0.astype(np.float64), w1.astype(np.float64)
+
+
+def upsample_bilinear2x(x):
+    """nn.Upsample(scale_factor=2, mode='bilinear') of torch 0.3.1 == align_corners=True   (tai.py:283,337,343;
+    slomo.py:113-149): weights as the library formed them (FP32), products and sums in float64."""
+    x = np.asarray(x, np.float64)
+    H, W = x.shape[-2:]
+    y0, y1, wy0, wy1 = upsample_bilinear2x_taps(H)
+    x0, x1, wx0, wx1 = upsample_bilinear2x_taps(W)
+    top = x[..., y0, :][..., :, x0] * wx0 + x[..., y0, :][..., :, x1] * wx1
+    bot = x[..., y1, :][..., :, x0] * wx0 + x[..., y1, :][..., :, x1] * wx1
+    return top * wy0[:, None] + bot * wy1[:, None]
+
+
+def upsample_bilinear2x_backward(g):
+    """Adjoint of upsample_bilinear2x: scatter every output gradient to its four taps (float64)."""
+    g = np.asarray(g, np.float64)
+    Ho, Wo = g.shape[-2:]
+    H, W = Ho // 2, Wo // 2
+    y0, y1, wy0, wy1 = upsample_bilinear2x_taps(H)
+    x0, x1, wx0, wx1 = upsample_bilinear2x_taps(W)
+    rows = np.zeros(g.shape[:-2] + (H, Wo))
+    np.add.at(rows, (Ellipsis, y0, slice(None)), g * wy0[:, None])
+    np.add.at(rows, (Ellipsis, y1, slice(None)), g * wy1[:, None])
+    out = np.zeros(g.shape[:-2] + (H, W))
+    rt = np.swapaxes(rows, -1, -2)  # [..., Wo, H]
+    ot = np.swapaxes(out, -1, -2)   # view [..., W, H]
+    np.add.at(ot, (Ellipsis, x0, slice(None)), rt * wx0[:, None])
+    np.add.at(ot, (Ellipsis, x1, slice(None)), rt * wx1[:, None])
+    return out
+
+
 def rel_err(x, ref):
     """max |x-ref| / max(|ref|, rms(ref)) -- the tolerance definition of SURVEY.md section 7
     (V/H are unnormalised and signed, so outputs have zero crossings)."""

@@ -10,7 +10,9 @@ on torch's CPU kernels), with every hot-path operator replaced by the reference'
   called once per stream after an explicit ReplicationPad2d, followed by the blend as three
   elementwise ops (tai.py:229-236, 105);
 * ConvLSTM gates          -> the chunk / sigmoid / tanh / cat chain of mcnet.py:287-293;
-* FlowWarper               -> host meshgrid + F.grid_sample with the torch-0.3.1 mapping (slomo.py:265-286).
+* FlowWarper               -> host meshgrid + F.grid_sample with the torch-0.3.1 mapping (slomo.py:265-286);
+* DecCnn unpool + add      -> the permute / cat / clone().zero_() chain of mcnet.py:240-256 and the add of 234-236;
+* nn.Upsample (bilinear)   -> F.interpolate(align_corners=True), the torch-0.3.1 mapping.
 
 Used by bench.py (``cpu_baseline`` and ``--impl reference``) and by tests as an end-to-end checker of
 the GPU model.  Never imported by the product package.
@@ -22,7 +24,8 @@ import torch.nn.functional as F
 from oracle import oracle as O
 from video_frame_inpainting_b200.discriminators.SNDiscriminator import SNDiscriminator
 from video_frame_inpainting_b200.losses.losses import GDL
-from video_frame_inpainting_b200.models.mcnet.mcnet import ConvLstmCell
+from video_frame_inpainting_b200.models.layers import BilinearUp2
+from video_frame_inpainting_b200.models.mcnet.mcnet import ConvLstmCell, DecCnn
 from video_frame_inpainting_b200.models.slomo.slomo import FlowWarper, SloMo
 from video_frame_inpainting_b200.models.tai.tai import TAI
 from video_frame_inpainting_b200.util.util import inverse_transform, weights_init
@@ -56,6 +59,23 @@ class CpuConvLstmCell(ConvLstmCell):
         new_c = c * torch.sigmoid(f + self.forget_bias) + torch.sigmoid(i) * torch.tanh(j)
         new_h = torch.tanh(new_c) * torch.sigmoid(o)
         return torch.cat((new_c, new_h), dim=1)
+
+
+class CpuDecCnn(DecCnn):
+    """fixed_unpooling as the reference spells it (mcnet.py:240-256) followed by the add (234-236)."""
+
+    def unpool_add(self, x, res):
+        x = x.permute(0, 2, 3, 1)
+        out = torch.cat((x, x.clone().zero_()), dim=3)
+        out = torch.cat((out, out.clone().zero_()), dim=2)
+        return out.view(x.size(0), 2 * x.size(1), 2 * x.size(2), x.size(3)).permute(0, 3, 1, 2) + res
+
+
+class CpuBilinearUp2(BilinearUp2):
+    """nn.Upsample(scale_factor=2, mode='bilinear') with the torch-0.3.1 mapping (align_corners=True today)."""
+
+    def forward(self, x):
+        return F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
 
 
 class CpuTAIMixin(object):
@@ -99,6 +119,10 @@ def to_cpu_reference(model):
             m.__class__ = CpuFlowWarper
         elif type(m) is SloMo:
             m.__class__ = CpuSloMo
+        elif type(m) is DecCnn:
+            m.__class__ = CpuDecCnn
+        elif type(m) is BilinearUp2:
+            m.__class__ = CpuBilinearUp2
         elif isinstance(m, TAI) and not isinstance(m, CpuTAIMixin):
             m.__class__ = type('Cpu' + type(m).__name__, (CpuTAIMixin, type(m)), {})
             m.separableConvolution = CpuSeparableConvolution.apply

@@ -153,3 +153,29 @@ def test_slomo_stage_formulas():
         assert np.allclose(a, -(1 - t) * t * f01 + t * t * f10) and np.allclose(b, (1 - t) ** 2 * f01 - t * (1 - t) * f10)
     assert O.time_weights(3) == [0.25, 0.5, 0.75]
     assert np.allclose(O.tai_blend(np.ones(3), 3 * np.ones(3)), 2.0)
+
+
+def test_upsample_and_unpool_against_torch():
+    """The decoder resampling oracles against the library ops the reference called (torch CPU, today's spelling
+    of the 0.3.1 mapping) and against the reference's own cat / permute spelling of fixed_unpooling."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(9)
+    for shape in [(2, 3, 5, 7), (1, 2, 1, 1), (1, 1, 16, 16), (2, 2, 3, 8)]:
+        x = rng.normal(size=shape).astype(np.float32)
+        xt = torch.from_numpy(x).double().requires_grad_()
+        y = F.interpolate(xt, scale_factor=2, mode='bilinear', align_corners=True)
+        assert O.rel_err(O.upsample_bilinear2x(x), y.detach().numpy()) < 2e-5   # FP32 weights vs float64 weights
+        g = rng.normal(size=y.shape)
+        y.backward(torch.from_numpy(g))
+        assert O.rel_err(O.upsample_bilinear2x_backward(g), xt.grad.numpy()) < 2e-5
+        # adjoint identity <up(x), g> == <x, up^T(g)>
+        assert abs(np.sum(O.upsample_bilinear2x(x) * g) - np.sum(x * O.upsample_bilinear2x_backward(g))) < 1e-9 * g.size
+        # mcnet.py:240-256 verbatim
+        p = torch.from_numpy(x).permute(0, 2, 3, 1)
+        out = torch.cat((p, p.clone().zero_()), dim=3)
+        out = torch.cat((out, out.clone().zero_()), dim=2)
+        ref = out.view(p.size(0), 2 * p.size(1), 2 * p.size(2), p.size(3)).permute(0, 3, 1, 2).numpy()
+        assert np.array_equal(O.fixed_unpooling(x), ref)
+    i0, i1, w0, w1 = O.upsample_bilinear2x_taps(16)
+    assert i0[0] == 0 and i1[-1] == 15 and i0[-1] == 15 and abs(w0[-1] + w1[-1] - 1) < 1e-7

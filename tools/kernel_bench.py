@@ -58,7 +58,21 @@ def main():
         print(json.dumps({"case": "ffma_probe", "packed": packed, "tflops": fl / best / 1e12,
                           "frac_nominal": fl / best / PEAK_FMA}), flush=True)
 
-    for name in args.cases.split(","):
+    if "resample" in args.cases.split(","):
+        for (B, C, H, W) in [(32, 64, 64, 64), (32, 128, 32, 32), (32, 32, 64, 64), (8, 64, 120, 160)]:
+            x, res, gr = U(B, C, H, W), U(B, C, 2 * H, 2 * W), U(B, C, 2 * H, 2 * W)
+            out_el = B * C * 4 * H * W
+            runs = {
+                "upsample2x_fwd": (lambda: ops.upsample_bilinear2x_forward(x), 4.0 * (out_el + out_el / 4)),
+                "upsample2x_bwd": (lambda: ops.upsample_bilinear2x_backward(gr), 4.0 * (out_el + out_el / 4)),
+                "unpool_add_fwd": (lambda: ops.unpool_add_forward(x, res), 4.0 * (2 * out_el + out_el / 4)),
+                "unpool_bwd": (lambda: ops.unpool_backward(gr), 4.0 * (out_el / 2)),
+            }
+            for k, (fn, by) in runs.items():
+                med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
+                print(json.dumps({"case": "resample", "shape": [B, C, H, W], "kernel": k, "ms_med": med * 1e3,
+                                  "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
+    for name in [c for c in args.cases.split(",") if c != "resample"]:
         B, C, Ho, Wo, ks = cases[name]
         I = U(B, C, Ho + ks - 1, Wo + ks - 1)
         P1, P2 = U(B, C, Ho, Wo), U(B, C, Ho, Wo)

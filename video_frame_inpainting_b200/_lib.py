@@ -36,6 +36,10 @@ SIGNATURES = {
     "flow_warp_backward_b200": (_c_i, [_c_f] * 5 + [_c_i] * 4 + [_c_s]),
     "slomo_flow_combine_warp_forward_b200": (_c_i, [_c_f] * 4 + [ctypes.c_double] + [_c_f] * 4 + [_c_i] * 4 + [_c_s]),
     "slomo_refine_blend_forward_b200": (_c_i, [_c_f] * 7 + [ctypes.c_double] + [_c_f] + [_c_i] * 4 + [_c_s]),
+    "upsample_bilinear2x_forward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
+    "upsample_bilinear2x_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
+    "unpool_add_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
+    "unpool_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "tai_b200_ffma_probe": (_c_i, [_c_f] + [_c_i] * 4 + [_c_s]),
 }
 

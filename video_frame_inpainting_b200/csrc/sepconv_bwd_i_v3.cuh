@@ -44,7 +44,8 @@ struct GiV3Cfg {
     static constexpr int DCOLS = TILE_W + KS - 1;    // destination columns per CTA
     static constexpr int WIN_FLOATS = DROWS * WCOLS;
     static constexpr int TS_PITCH = FNX + 1;
-    static constexpr int TS_FLOATS = KS * TS_PITCH;
+    static constexpr int TS_PAD = FNX - 1;                               // zero rows j = -7..-1 and KS..KS+6
+    static constexpr int TS_FLOATS = (KS + 2 * TS_PAD) * TS_PITCH + 8;   // so that the diagonal reads need no predicates
     static constexpr int NBAR = 1 + NCHUNK;
     static constexpr size_t smem_bytes() { return (size_t)(SLAB_FLOATS + WX * (WIN_FLOATS + TS_FLOATS)) * 4 + 8 * NBAR; }
 };
@@ -54,17 +55,53 @@ struct GiV3Maps {
     CUtensorMap v;  // box {32, 8, CH_TAPS, 1}
 };
 
-// One destination row: source rows [RLO, RHI) of this thread reach it (0 <= yy - r < KS).
-template <int KS, int RLO, int RHI>
+// Anti-diagonal sums of one staged row: destination column d receives ts[d - c][c], c = 0..7.
+// Split in two so that the 16 shared-memory loads are in flight underneath the next row's FMAs.
+template <int KS>
+struct GiDiag {
+    float a[2][FNX];
+};
+template <int KS>
+__device__ __forceinline__ void gi_diag_load(const float *ts, int lane, GiDiag<KS> &g)
+{
+    using Cfg = GiV3Cfg<KS>;
+    // ts points at row j = 0; rows -7..-1 and KS..KS+6 are zero.  Lanes whose second column does not exist
+    // (lane + 32 >= WCOLS) read their first column twice; the result is not stored.
+    const int d0 = (lane < Cfg::WCOLS) ? lane : 0, d1 = (lane + 32 < Cfg::WCOLS) ? lane + 32 : d0;
+    const float *p0 = ts + d0 * Cfg::TS_PITCH, *p1 = ts + d1 * Cfg::TS_PITCH;
+#pragma unroll
+    for (int c = 0; c < FNX; ++c) {
+        g.a[0][c] = p0[c * (1 - Cfg::TS_PITCH)];
+        g.a[1][c] = p1[c * (1 - Cfg::TS_PITCH)];
+    }
+}
+template <int KS>
+__device__ __forceinline__ void gi_diag_store(const GiDiag<KS> &g, float *wrow, int lane)
+{
+    using Cfg = GiV3Cfg<KS>;
+    float s0 = (g.a[0][0] + g.a[0][1]) + (g.a[0][2] + g.a[0][3]);
+    float s1 = (g.a[1][0] + g.a[1][1]) + (g.a[1][2] + g.a[1][3]);
+    s0 += (g.a[0][4] + g.a[0][5]) + (g.a[0][6] + g.a[0][7]);
+    s1 += (g.a[1][4] + g.a[1][5]) + (g.a[1][6] + g.a[1][7]);
+    if (lane < Cfg::WCOLS) wrow[lane] = s0;
+    if (lane + 32 < Cfg::WCOLS) wrow[lane + 32] = s1;
+}
+
+// One destination row yy: source rows [RLO, RHI) of this thread reach it (0 <= yy - r < KS).
+// Software pipeline over rows: while the 8 x J FMAs of row yy run, the staged values of row yy-1 are on
+// their way from shared memory; they are summed and written to the window after the FMAs, then (all lanes
+// have consumed the staging buffer: first __syncwarp) row yy is staged (second __syncwarp: visible).
+template <int KS, int RLO, int RHI, bool HAS_PREV>
 __device__ __forceinline__ void gi_row_v3(const float *__restrict__ vrow, const float (&h)[FP][(KS + 3) / 4],
-                                          const float (&go)[FP], float *__restrict__ ts, float *__restrict__ wrow,
-                                          int cx, int ch, int lane)
+                                          const float (&go)[FP], float *ts, float *wrow_prev, int cx, int ch, int lane)
 {
     using Cfg = GiV3Cfg<KS>;
     constexpr int J = Cfg::J;
     float vg[FP];
 #pragma unroll
     for (int r = RLO; r < RHI; ++r) vg[r] = vrow[r * (Cfg::TILE_W - Cfg::VROW)] * go[r];  // tap yy-r of source row r
+    GiDiag<KS> g;
+    if (HAS_PREV) gi_diag_load<KS>(ts, lane, g);
     float t[J];
 #pragma unroll
     for (int jj = 0; jj < J; ++jj) t[jj] = vg[RLO] * h[RLO][jj];
@@ -72,24 +109,14 @@ __device__ __forceinline__ void gi_row_v3(const float *__restrict__ vrow, const 
     for (int r = RLO + 1; r < RHI; ++r)
 #pragma unroll
         for (int jj = 0; jj < J; ++jj) t[jj] = fmaf(vg[r], h[r][jj], t[jj]);
+    if (HAS_PREV) {
+        gi_diag_store<KS>(g, wrow_prev, lane);
+        __syncwarp();
+    }
     // stage: ts[j][cx]
 #pragma unroll
     for (int jj = 0; jj < J; ++jj)
         if (ch + 4 * jj < KS) ts[(ch + 4 * jj) * Cfg::TS_PITCH + cx] = t[jj];
-    __syncwarp();
-    // anti-diagonal sums: destination column d receives ts[d - c][c], c = 0..7
-    {
-        const int d0 = lane, d1 = lane + 32;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < FNX; ++c) {
-            const int j0 = d0 - c, j1 = d1 - c;
-            if (j0 >= 0 && j0 < KS) s0 += ts[j0 * Cfg::TS_PITCH + c];
-            if (j1 < KS && d1 < Cfg::WCOLS) s1 += ts[j1 * Cfg::TS_PITCH + c];
-        }
-        if (d0 < Cfg::WCOLS) wrow[d0] = s0;
-        if (d1 < Cfg::WCOLS) wrow[d1] = s1;
-    }
     __syncwarp();
 }
 
@@ -111,7 +138,7 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cx = lane & 7, ch = lane >> 3;
     const int ntiles = p.B * p.nty * p.ntx;
-    float *ts = tsb + warp * Cfg::TS_FLOATS;
+    float *ts = tsb + warp * Cfg::TS_FLOATS + Cfg::TS_PAD * Cfg::TS_PITCH;  // row j = 0
     float *mywin = win + warp * Cfg::WIN_FLOATS;
 
     if (threadIdx.x == 0) {
@@ -119,6 +146,7 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
+    for (int i = threadIdx.x; i < Cfg::WX * Cfg::TS_FLOATS; i += Cfg::NT) tsb[i] = 0.f;
     __syncthreads();
     uint32_t parity = 0;
 
@@ -179,7 +207,9 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
             }
             static_for<0, FP - 1>([&](auto YY) {
                 constexpr int yy = decltype(YY)::value;
-                gi_row_v3<KS, 0, yy + 1>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);
+                gi_row_v3<KS, 0, yy + 1, (yy > 0)>(vrow + yy * Cfg::VROW, h, go, ts,
+                                                   mywin + (yy - 1) * Cfg::WCOLS, cx, ch,
+                                                   lane);
             });
 #pragma unroll
             for (int q = 0; q < Cfg::NCHUNK; ++q) {
@@ -188,13 +218,20 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
                 if (q >= PRO_CHUNKS && c == 0) mbar_wait(&bars[1 + q], parity);
 #pragma unroll 1
                 for (int yy = lo; yy < hi; ++yy)
-                    gi_row_v3<KS, 0, FP>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx, ch, lane);
+                    gi_row_v3<KS, 0, FP, true>(vrow + yy * Cfg::VROW, h, go, ts,
+                                               mywin + (yy - 1) * Cfg::WCOLS, cx, ch, lane);
             }
             static_for<0, FP - 1>([&](auto E) {
                 constexpr int yy = KS + decltype(E)::value;
-                gi_row_v3<KS, decltype(E)::value + 1, FP>(vrow + yy * Cfg::VROW, h, go, ts, mywin + yy * Cfg::WCOLS, cx,
-                                                         ch, lane);
+                gi_row_v3<KS, decltype(E)::value + 1, FP, true>(vrow + yy * Cfg::VROW, h, go, ts,
+                                                               mywin + (yy - 1) * Cfg::WCOLS, cx, ch, lane);
             });
+            {   // drain the pipeline: the last destination row
+                constexpr int yy = Cfg::DROWS - 1;
+                GiDiag<KS> g;
+                gi_diag_load<KS>(ts, lane, g);
+                gi_diag_store<KS>(g, mywin + yy * Cfg::WCOLS, lane);
+            }
             __syncthreads();  // all four windows are complete
 
             // ---- merge the four warp windows and add the tile's destination window into gI ----

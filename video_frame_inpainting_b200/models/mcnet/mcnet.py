@@ -101,9 +101,13 @@ class DecCnn(nn.Module):
         self.dec1 = nn.Sequential(*_conv_relu_chain([gf_dim, gf_dim, c_dim], 3, transposed=True, last=nn.Tanh()))
 
     def forward(self, comb, res1, res2, res3):
-        dec3_out = self.dec3(self.fixed_unpooling(comb) + res3)
-        dec2_out = self.dec2(self.fixed_unpooling(dec3_out) + res2)
-        return self.dec1(self.fixed_unpooling(dec2_out) + res1)
+        dec3_out = self.dec3(self.unpool_add(comb, res3))
+        dec2_out = self.dec2(self.unpool_add(dec3_out, res2))
+        return self.dec1(self.unpool_add(dec2_out, res1))
+
+    def unpool_add(self, x, res):
+        """``fixed_unpooling(x) + res`` (mcnet.py:234-236) as one kernel."""
+        return ops.UnpoolAddFunction.apply(x.contiguous(), res.contiguous())
 
     def fixed_unpooling(self, x):
         """out[2y, 2x] = x[y, x], the other three elements of every 2x2 cell are zero (mcnet.py:240-256;

@@ -20,10 +20,11 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ..layers import BilinearUp2
 
 
 def _up2():
-    return nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)  # torch-0.3.1 bilinear mapping
+    return BilinearUp2()  # torch-0.3.1 bilinear mapping (align corners), one kernel of this library
 
 
 def _stage(cin, cmid, cout, k, alpha, pool):

@@ -23,12 +23,13 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from ... import ops
+from ..layers import BilinearUp2
 from ...separable_convolution.SeparableConvolution import SeparableConvolution
 from ..mcnet.mcnet import MCNet, Residual, gray_difference_frames
 
 
 def _up2():
-    return nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+    return BilinearUp2()  # torch-0.3.1 bilinear mapping (align corners), one kernel of this library
 
 
 class TAIFillInModel(nn.Module):

@@ -234,6 +234,78 @@ class ConvLstmGatesFunction(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# decoder resampling
+# ------------------------------------------------------------------------------------------------
+
+def upsample_bilinear2x_forward(x):
+    dev = _check("upsample_bilinear2x_forward", x)
+    B, C, H, W = x.shape
+    with torch.cuda.device(dev):
+        out = torch.empty(B, C, 2 * H, 2 * W, device=dev, dtype=torch.float32)
+        _lib.call("upsample_bilinear2x_forward_b200", _ptr(x), _ptr(out), B * C, H, W, _stream())
+    return out
+
+
+def upsample_bilinear2x_backward(grad_out):
+    dev = _check("upsample_bilinear2x_backward", grad_out)
+    B, C, Ho, Wo = grad_out.shape
+    assert Ho % 2 == 0 and Wo % 2 == 0
+    with torch.cuda.device(dev):
+        gin = torch.empty(B, C, Ho // 2, Wo // 2, device=dev, dtype=torch.float32)
+        _lib.call("upsample_bilinear2x_backward_b200", _ptr(grad_out), _ptr(gin), B * C, Ho // 2, Wo // 2, _stream())
+    return gin
+
+
+class UpsampleBilinear2xFunction(torch.autograd.Function):
+    """apply(x[B,C,H,W]) -> [B,C,2H,2W]: nn.Upsample(scale_factor=2, mode='bilinear') with the torch-0.3.1
+    (align-corners) mapping   (tai.py:283,337,343; slomo.py:113-149)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return upsample_bilinear2x_forward(x)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        return upsample_bilinear2x_backward(grad_out.contiguous())
+
+
+def unpool_add_forward(x, res):
+    dev = _check("unpool_add_forward", x, res)
+    B, C, H, W = x.shape
+    assert res.shape == (B, C, 2 * H, 2 * W), "residual must be [B, C, 2H, 2W]"
+    with torch.cuda.device(dev):
+        out = torch.empty_like(res)
+        _lib.call("unpool_add_forward_b200", _ptr(x), _ptr(res), _ptr(out), B * C, H, W, _stream())
+    return out
+
+
+def unpool_backward(grad_out):
+    dev = _check("unpool_backward", grad_out)
+    B, C, Ho, Wo = grad_out.shape
+    with torch.cuda.device(dev):
+        gx = torch.empty(B, C, Ho // 2, Wo // 2, device=dev, dtype=torch.float32)
+        _lib.call("unpool_backward_b200", _ptr(grad_out), _ptr(gx), B * C, Ho // 2, Wo // 2, _stream())
+    return gx
+
+
+class UnpoolAddFunction(torch.autograd.Function):
+    """apply(x[B,C,H,W], res[B,C,2H,2W]) -> fixed_unpooling(x) + res   (mcnet.py:234-236,240-256)."""
+
+    @staticmethod
+    def forward(ctx, x, res):
+        ctx.needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return unpool_add_forward(x, res)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        grad_out = grad_out.contiguous()
+        gx = unpool_backward(grad_out) if ctx.needs[0] else None
+        return gx, (grad_out if ctx.needs[1] else None)
+
+
+# ------------------------------------------------------------------------------------------------
 # Super SloMo warp / blend
 # ------------------------------------------------------------------------------------------------
 
