@@ -77,18 +77,24 @@ __device__ __forceinline__ void vh_row_v3(const float *__restrict__ srow, const 
         float iv[J];
 #pragma unroll
         for (int jj = 0; jj < J; ++jj) iv[jj] = srow[c * CSTRIDE + 4 * jj];
+        // tap-outer order: the row sums s[r] are serial FMA chains; interleaving the rows (and the independent
+        // a[r][jj] updates) keeps dependent FMAs 2*(RHI-RLO) issue slots apart
+        float w[BP], s[BP];
 #pragma unroll
         for (int r = RLO; r < RHI; ++r) {
-            const float w = v[r] * go[c][r];
-            float s = h[r][0] * iv[0];
-            a[r][0] = fmaf(w, iv[0], a[r][0]);
-#pragma unroll
-            for (int jj = 1; jj < J; ++jj) {
-                s = fmaf(h[r][jj], iv[jj], s);
-                a[r][jj] = fmaf(w, iv[jj], a[r][jj]);
-            }
-            tsum[r] = fmaf(go[c][r], s, tsum[r]);
+            w[r] = v[r] * go[c][r];
+            s[r] = h[r][0] * iv[0];
+            a[r][0] = fmaf(w[r], iv[0], a[r][0]);
         }
+#pragma unroll
+        for (int jj = 1; jj < J; ++jj)
+#pragma unroll
+            for (int r = RLO; r < RHI; ++r) {
+                s[r] = fmaf(h[r][jj], iv[jj], s[r]);
+                a[r][jj] = fmaf(w[r], iv[jj], a[r][jj]);
+            }
+#pragma unroll
+        for (int r = RLO; r < RHI; ++r) tsum[r] = fmaf(go[c][r], s[r], tsum[r]);
     }
 }
 
