@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in the cuDNN convolutions (reported in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -183,7 +184,7 @@ def run_reference(args):
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
 
-def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0):
+def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0, graph=True):
     """Model + environment + synthetic clips of a named workload on cuda:local_rank.
     Returns (step_resident, step_e2e, info)."""
     import torch
@@ -211,6 +212,7 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0):
     else:
         env = BaseVideoFillInEnvironment(model, "/tmp/tai_b200_ckpt", "bench", (0, 0))
         env.eval()
+        env.enable_cuda_graph(bool(graph))  # replay of the captured forward; the training step stays eager
     env.K, env.T, env.F = K, T, F_
 
     g = torch.Generator().manual_seed(1000 + rank)  # different clips per rank
@@ -241,7 +243,7 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0):
 
     h2d = (h_pre.numel() + h_fol.numel() + (h_mid.numel() if training else 0)) * 4
     info = dict(key=key, c=c, H=H, W=W, K=K, T=T, F=F_, B=B, training=training, h2d=h2d,
-                d2h=(10 if training else 1) * 4, env=env)
+                d2h=(10 if training else 1) * 4, env=env, graph=bool(graph) and not training)
     return step_resident, step_e2e, info
 
 
@@ -264,7 +266,8 @@ def run_b200(args):
     rank, local_rank, world = init_distributed()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    step_resident, step_e2e, info = build_workload(args.workload, args.batch, args.tf32, rank, local_rank)
+    step_resident, step_e2e, info = build_workload(args.workload, args.batch, args.tf32, rank, local_rank,
+                                                   graph=not args.no_graph)
     key, c, H, W, K, T, F_, B, training = (info[k] for k in ("key", "c", "H", "W", "K", "T", "F", "B", "training"))
 
     def barrier():
@@ -290,12 +293,32 @@ def run_b200(args):
         step_resident()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = _lib.launch_count()
-    _lib.timing_enable(True)
-    ms = timed(step_resident, args.steps)
-    kernel_times = _lib.timing_report()
-    _lib.timing_enable(False)
-    launches = _lib.launch_count() - launches0
+    if info["graph"]:
+        # Kernels replayed from a CUDA graph are not re-issued by the library, so its launch counter and event
+        # timers see nothing: count / time them in ONE eager pass (same kernels, same order), then time replays.
+        env = info["env"]
+        saved, env._graphs = env._graphs, None
+        launches0 = _lib.launch_count()
+        _lib.timing_enable(True)
+        step_resident()
+        torch.cuda.synchronize()
+        kernel_times = _lib.timing_report()
+        _lib.timing_enable(False)
+        per_step_launches = _lib.launch_count() - launches0
+        for k in kernel_times:                      # scale the single pass to the timed region
+            for f in ("ms", "launches", "flops", "bytes"):
+                k[f] *= args.steps
+        env._graphs = saved
+        step_resident()                              # capture
+        ms = timed(step_resident, args.steps)
+        launches = per_step_launches * args.steps
+    else:
+        launches0 = _lib.launch_count()
+        _lib.timing_enable(True)
+        ms = timed(step_resident, args.steps)
+        kernel_times = _lib.timing_report()
+        _lib.timing_enable(False)
+        launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
 
     step_e2e()  # warm the pinned-copy path
@@ -361,12 +384,13 @@ def run_b200(args):
                         "sample": sample + "; single un-warmed step, %.1f s" % dt}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC if training else "bi-TAI inpainted frames/sec (inference forward pass, %s)" % args.workload, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "model_key": key, "clips_per_gpu": B, "global_clips": B * world,
                    "frame": [c, H, W], "K": K, "T": T, "F": F_, "training": training, "ks": 51,
                    "conv_math": "tf32" if args.tf32 else "fp32 (cudnn.allow_tf32=False)",
+                   "launch": "cuda-graph replay of the forward pass" if info["graph"] else "eager",
                    "parallelism": "dp%d (clips sharded, NCCL all-reduce of gradients only)" % world,
                    "l2": "per-step working set (activations, 4 x 107 MB kernel maps per middle frame) >> 126 MB L2"},
         "clocks": clocks,

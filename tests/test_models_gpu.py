@@ -86,3 +86,46 @@ def test_training_environment_step_runs_and_updates(cuda):
     snap = torch.load("/tmp/tai_b200_test/t/model_latest.ckpt", map_location="cpu")
     assert set(snap) == {'updates', 'sum_avg_psnr_err', 'sum_avg_ssim_err', 'generator', 'optimizer_G',
                          'discriminator', 'optimizer_D'}  # environments.py:186-194, 290-297
+
+
+@pytest.mark.parametrize("key", ["tai", "slomo"])
+def test_cuda_graph_replay_matches_eager_forward(cuda, key):
+    """forward_test through a captured CUDA graph (static buffers, replayed for new inputs) returns what the
+    eager launch sequence returns -- the library's entry points are capturable (no allocation, no host sync)."""
+    from video_frame_inpainting_b200.environments.environments import BaseVideoFillInEnvironment
+    _strict_fp32()
+    torch.manual_seed(3)
+    if key == "tai":
+        model, c = TAIFillInModel(8, 1, 3, 13, num_block=5, kf_dim=4), 1
+    else:
+        model, c = SloMoFillInModel(8, 3), 3
+    env = BaseVideoFillInEnvironment(model, "/tmp/tai_b200_ckpt", "graph_test", (0, 0))
+    env.eval()
+    env.T = 2
+    clips = [(torch.rand(1, 3, c, 32, 64) * 2 - 1, torch.rand(1, 3, c, 32, 64) * 2 - 1) for _ in range(3)]
+    eager = []
+    for pre, fol in clips:
+        env.set_test_inputs(pre, fol)
+        env.forward_test()
+        eager.append(env.gen_output['pred'].clone())
+    env.enable_cuda_graph(True)
+    for (pre, fol), ref in zip(clips, eager):
+        env.set_test_inputs(pre, fol)
+        env.forward_test()
+        torch.cuda.synchronize()
+        err = O.rel_err(env.gen_output['pred'].cpu().numpy(), ref.cpu().numpy())
+        # cuDNN picks other convolution algorithms under stream capture: the same tolerance as the GPU-vs-CPU
+        # model parity above (2e-3); stale buffers would show up as O(1)
+        assert err < 2e-3, "graph replay differs from eager: rel err %.3e" % err
+    assert len(env._graphs) == 1  # one capture, three replays
+    # the static buffers really are refreshed: another input gives another result, the first input its own again
+    # (cuDNN's small-shape algorithms are not run-to-run bit-identical, hence tolerances instead of equality)
+    env.set_test_inputs(*clips[0])
+    env.forward_test()
+    first = env.gen_output['pred'].clone().cpu().numpy()
+    env.set_test_inputs(*clips[1])
+    env.forward_test()
+    assert O.rel_err(env.gen_output['pred'].cpu().numpy(), first) > 1e-2
+    env.set_test_inputs(*clips[0])
+    env.forward_test()
+    assert O.rel_err(env.gen_output['pred'].cpu().numpy(), first) < 2e-3
