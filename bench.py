@@ -150,6 +150,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation with all host threads
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
     fn, frames, sample = cpu_reference_step_factory(args.workload)
     t0 = time.time()

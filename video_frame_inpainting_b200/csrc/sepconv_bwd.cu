@@ -281,24 +281,49 @@ __global__ void reppad_fwd_kernel(const float *__restrict__ in, float *__restric
 }
 
 // Adjoint: every unpadded element sums the padded elements that were copied from it (fixed order,
-// deterministic -- no atomics).
-__global__ void reppad_bwd_kernel(const float *__restrict__ gpad, float *__restrict__ gin, int N, int H, int W, int pad)
+// deterministic -- no atomics).  One warp per unpadded row: the lanes sum the source rows column by column
+// (coalesced; one source row for an interior output row, pad+1 for the first / last one), interior columns
+// are stored directly and the pad+1 columns of each border are combined with a shuffle tree.  (A thread per
+// output element leaves the four corner threads with (pad+1)^2 serial loads: 51 us for 4 MB at pad = 25.)
+__global__ void __launch_bounds__(256)
+reppad_bwd_kernel(const float *__restrict__ gpad, float *__restrict__ gin, int N, int H, int W, int pad)
 {
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-    const long n = (long)N * H * W;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
-        const int x = idx % W;
-        const int y = (idx / W) % H;
-        const long img = idx / ((long)W * H);
-        int ylo = y + pad, yhi = y + pad, xlo = x + pad, xhi = x + pad;
-        if (y == 0) ylo = 0;
-        if (y == H - 1) yhi = Hp - 1;
-        if (x == 0) xlo = 0;
-        if (x == W - 1) xhi = Wp - 1;
-        float acc = 0.f;
-        for (int yy = ylo; yy <= yhi; ++yy)
-            for (int xx = xlo; xx <= xhi; ++xx) acc += gpad[(img * Hp + yy) * Wp + xx];
-        gin[idx] = acc;
+    const int lane = threadIdx.x & 31;
+    const long nrows = (long)N * H;
+    for (long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows;
+         row += (long)gridDim.x * (blockDim.x >> 5)) {
+        const int y = (int)(row % H);
+        const long img = row / H;
+        const int ylo = (y == 0) ? 0 : y + pad;
+        const int yhi = (y == H - 1) ? Hp - 1 : y + pad;
+        const float *src = gpad + (img * Hp + ylo) * Wp;
+        float *dst = gin + row * W;
+        float left = 0.f, right = 0.f;
+        for (int xx = lane; xx < Wp; xx += 32) {
+            float cs = 0.f;
+            for (int yy = 0; yy <= yhi - ylo; ++yy) cs += __ldg(src + (long)yy * Wp + xx);
+            const int x = xx - pad;
+            if (x <= 0)
+                left += cs;            // padded columns 0 .. pad feed output column 0
+            else if (x >= W - 1)
+                right += cs;           // padded columns W-1+pad .. Wp-1 feed output column W-1
+            else
+                dst[x] = cs;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            left += __shfl_xor_sync(0xffffffffu, left, o);
+            right += __shfl_xor_sync(0xffffffffu, right, o);
+        }
+        if (lane == 0) {
+            if (W == 1) {
+                dst[0] = left + right;
+            } else {
+                dst[0] = left;
+                dst[W - 1] = right;
+            }
+        }
     }
 }
 
@@ -595,7 +620,7 @@ extern "C" int tai_fused_backward_b200(const float *grad_pred, const float *grad
             if (rc == TAI_OK) {
                 {
                     TimingScope ts("reppad_bwd", st, 0.0, 4.0 * ((double)B * C * (H + ks - 1) * (W + ks - 1) + n));
-                    reppad_bwd_kernel<<<ew_grid(n, 256), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
+                    reppad_bwd_kernel<<<ew_grid((long)B * C * H * 32, 256), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
                 }
                 rc = check_launch("reppad_bwd_kernel");
             }
@@ -621,6 +646,6 @@ extern "C" int replication_pad_backward_b200(const float *grad_out, float *grad_
     const long n = (long)N * H * W;
     TAI_REQUIRE(fits_int31((long)N * (H + 2 * p) * (W + 2 * p)), TAI_ERR_TOO_LARGE,
                 "replication_pad_backward_b200: tensor has >= 2^31 elements");
-    reppad_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, N, H, W, p);
+    reppad_bwd_kernel<<<ew_grid((long)N * H * 32, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, N, H, W, p);
     return check_launch("reppad_bwd_kernel");
 }

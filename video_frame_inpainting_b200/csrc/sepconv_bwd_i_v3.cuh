@@ -17,9 +17,12 @@
 //     is this lane's contribution to destination column cx + j of that row;
 //   * the 4 x 13 values of a pixel column group are staged in shared memory and summed along the
 //     anti-diagonals cx + j = const (8 terms) by the warp itself: 58 destination columns per warp-row;
-//   * each warp keeps a private 58 x 58 destination window; after the sweep the CTA merges its four
-//     windows (they overlap by 50 columns) and adds the 58 x 82 result into gI with red.global
-//     (neighbouring tiles overlap by ks-1 rows/columns, so gI is zeroed by the launcher first).
+//   * each warp keeps a private ROLLING window of two 8-row groups x 58 destination columns; whenever the
+//     four warps have completed a group (one __syncthreads per 8 destination rows) the CTA merges the four
+//     windows of that group (they overlap by 50 columns) and adds the 8 x 82 result into gI with red.global
+//     while the sweep carries on into the other buffer (neighbouring tiles overlap by ks-1 rows/columns, so
+//     gI is zeroed by the launcher first).  A full 58 x 58 window per warp (the first version) cost 54 KB of
+//     shared memory and held the kernel at two CTAs per SM; the rolling window needs 15 KB: three CTAs.
 #pragma once
 
 #include "common.cuh"
@@ -42,7 +45,9 @@ struct GiV3Cfg {
     static constexpr int DROWS = TILE_H + KS - 1;    // destination rows per tile
     static constexpr int WCOLS = FNX + KS - 1;       // destination columns per warp
     static constexpr int DCOLS = TILE_W + KS - 1;    // destination columns per CTA
-    static constexpr int WIN_FLOATS = DROWS * WCOLS;
+    static constexpr int GROWS = 8;                  // destination rows per flush group
+    static constexpr int NGROUPS = (DROWS + GROWS - 1) / GROWS;
+    static constexpr int WIN_FLOATS = 2 * GROWS * WCOLS;  // per warp: two groups (one being written, one being flushed)
     static constexpr int TS_PITCH = FNX + 1;
     static constexpr int TS_PAD = FNX - 1;                               // zero rows j = -7..-1 and KS..KS+6
     static constexpr int TS_FLOATS = (KS + 2 * TS_PAD) * TS_PITCH + 8;   // so that the diagonal reads need no predicates
@@ -121,7 +126,7 @@ __device__ __forceinline__ void gi_row_v3(const float *__restrict__ vrow, const 
 }
 
 template <int KS>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 3)
 sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p)
 {
     using Cfg = GiV3Cfg<KS>;
@@ -129,7 +134,7 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
     static_assert(Cfg::WCOLS <= 64, "two destination columns per lane");
     extern __shared__ __align__(128) float smem[];
     float *slab = smem;
-    float *win = smem + Cfg::SLAB_FLOATS;                       // [4 warps][DROWS][WCOLS]
+    float *win = smem + Cfg::SLAB_FLOATS;                       // [4 warps][2 groups][GROWS][WCOLS]
     float *tsb = win + Cfg::WX * Cfg::WIN_FLOATS;               // [4 warps][KS][TS_PITCH]
     uint64_t *bars = reinterpret_cast<uint64_t *>(tsb + Cfg::WX * Cfg::TS_FLOATS);
 
@@ -193,8 +198,33 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
             }
         }
         const float *vrow = slab + warp * FNX + cx;
+        auto wrow = [&](int yy) {  // this warp's window row of destination row yy (rolling: group parity, row in group)
+            return mywin + (((yy >> 3) & 1) * Cfg::GROWS + (yy & 7)) * Cfg::WCOLS;
+        };
 
         for (int c = 0; c < p.C; ++c) {
+            float *gdst = p.gin + ((long)(b * p.C + c) * Hi + y0) * Wi + x0;
+            // Merge group g of the four warp windows and add it into gI.  Every thread calls it at the same
+            // point of the sweep; the barrier also separates this group's buffer from its reuse two groups later.
+            auto flush = [&](int g) {
+                __syncthreads();
+                const int D = threadIdx.x;
+                if (D < Cfg::DCOLS && x0 + D < Wi) {
+                    const float *wb = win + (g & 1) * Cfg::GROWS * Cfg::WCOLS;
+                    const int nrow = min(Cfg::GROWS, Cfg::DROWS - g * Cfg::GROWS);
+                    for (int r = 0; r < nrow; ++r) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int w = 0; w < Cfg::WX; ++w) {
+                            const int dc = D - w * FNX;
+                            if (dc >= 0 && dc < Cfg::WCOLS) sum += wb[w * Cfg::WIN_FLOATS + r * Cfg::WCOLS + dc];
+                        }
+                        const int yy = g * Cfg::GROWS + r;
+                        if (y0 + yy < Hi) atomicAdd(gdst + (long)yy * Wi + D, sum);
+                    }
+                }
+            };
+
             float go[FP];
 #pragma unroll
             for (int r = 0; r < FP; ++r)
@@ -207,9 +237,7 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
             }
             static_for<0, FP - 1>([&](auto YY) {
                 constexpr int yy = decltype(YY)::value;
-                gi_row_v3<KS, 0, yy + 1, (yy > 0)>(vrow + yy * Cfg::VROW, h, go, ts,
-                                                   mywin + (yy - 1) * Cfg::WCOLS, cx, ch,
-                                                   lane);
+                gi_row_v3<KS, 0, yy + 1, (yy > 0)>(vrow + yy * Cfg::VROW, h, go, ts, wrow(yy - 1), cx, ch, lane);
             });
 #pragma unroll
             for (int q = 0; q < Cfg::NCHUNK; ++q) {
@@ -217,36 +245,24 @@ sepconv_bwd_i_v3_kernel(const __grid_constant__ GiV3Maps maps, const BwdParams p
                 const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
                 if (q >= PRO_CHUNKS && c == 0) mbar_wait(&bars[1 + q], parity);
 #pragma unroll 1
-                for (int yy = lo; yy < hi; ++yy)
-                    gi_row_v3<KS, 0, FP, true>(vrow + yy * Cfg::VROW, h, go, ts,
-                                               mywin + (yy - 1) * Cfg::WCOLS, cx, ch, lane);
+                for (int yy = lo; yy < hi; ++yy) {
+                    gi_row_v3<KS, 0, FP, true>(vrow + yy * Cfg::VROW, h, go, ts, wrow(yy - 1), cx, ch, lane);
+                    if ((yy & 7) == 0) flush((yy >> 3) - 1);  // row yy-1, the last of its group, has just been stored
+                }
             }
             static_for<0, FP - 1>([&](auto E) {
                 constexpr int yy = KS + decltype(E)::value;
-                gi_row_v3<KS, decltype(E)::value + 1, FP, true>(vrow + yy * Cfg::VROW, h, go, ts,
-                                                               mywin + (yy - 1) * Cfg::WCOLS, cx, ch, lane);
+                gi_row_v3<KS, decltype(E)::value + 1, FP, true>(vrow + yy * Cfg::VROW, h, go, ts, wrow(yy - 1), cx, ch,
+                                                               lane);
+                if ((yy & 7) == 0) flush((yy >> 3) - 1);
             });
-            {   // drain the pipeline: the last destination row
+            {   // drain the pipeline: the last destination row, then the last group
                 constexpr int yy = Cfg::DROWS - 1;
                 GiDiag<KS> g;
                 gi_diag_load<KS>(ts, lane, g);
-                gi_diag_store<KS>(g, mywin + yy * Cfg::WCOLS, lane);
+                gi_diag_store<KS>(g, wrow(yy), lane);
+                flush(yy >> 3);
             }
-            __syncthreads();  // all four windows are complete
-
-            // ---- merge the four warp windows and add the tile's destination window into gI ----
-            float *gdst = p.gin + ((long)(b * p.C + c) * Hi + y0) * Wi + x0;
-            for (int idx = threadIdx.x; idx < Cfg::DROWS * Cfg::DCOLS; idx += Cfg::NT) {
-                const int yy = idx / Cfg::DCOLS, D = idx - yy * Cfg::DCOLS;
-                float sum = 0.f;
-#pragma unroll
-                for (int w = 0; w < Cfg::WX; ++w) {
-                    const int dc = D - w * FNX;
-                    if (dc >= 0 && dc < Cfg::WCOLS) sum += win[w * Cfg::WIN_FLOATS + yy * Cfg::WCOLS + dc];
-                }
-                if (y0 + yy < Hi && x0 + D < Wi) atomicAdd(gdst + (long)yy * Wi + D, sum);
-            }
-            __syncthreads();  // windows are free for the next channel / tile
         }
         parity ^= 1;
     }
