@@ -15,6 +15,7 @@ namespace tai {
 
 static inline unsigned resample_grid(long work_items, int block)
 {
+    // grid-stride over 16 CTAs per SM (measured: an uncapped one-item-per-thread grid is 7-15 % slower here)
     long g = (work_items + block - 1) / block;
     const long cap = (long)sm_count() * 16;
     if (g > cap) g = cap;
@@ -73,9 +74,21 @@ upsample2x_fwd_kernel(const float *__restrict__ in, float *__restrict__ out, int
     {   // stage the input tile: 64 threads per row (two passes cover the <= 67 columns), 4 rows at a time
         const float *src = in + (n * H + r_lo) * W + c_lo;
         const int c = threadIdx.x & 63;
-        for (int r = threadIdx.x >> 6; r < nr; r += UF_NT / 64) {
-            if (c < nc) s_in[r][c] = __ldg(src + (long)r * W + c);
-            if (c + 64 < nc) s_in[r][c + 64] = __ldg(src + (long)r * W + c + 64);
+        constexpr int NIT = (UF_IR + UF_NT / 64 - 1) / (UF_NT / 64);
+        float a[NIT], b[NIT];
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {  // every load is in flight before the first store
+            const int r = (threadIdx.x >> 6) + k * (UF_NT / 64);
+            a[k] = (r < nr && c < nc) ? __ldg(src + (long)r * W + c) : 0.f;
+            b[k] = (r < nr && c + 64 < nc) ? __ldg(src + (long)r * W + c + 64) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {
+            const int r = (threadIdx.x >> 6) + k * (UF_NT / 64);
+            if (r < nr) {
+                s_in[r][c] = a[k];
+                if (c + 64 < UF_IC + 1) s_in[r][c + 64] = b[k];
+            }
         }
     }
     __syncthreads();
@@ -173,20 +186,25 @@ upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, i
         const int ox = oxb + 2 * cp;
         const bool pair_ok = (Wo % 2 == 0) && ox >= 0 && ox + 1 < Wo && ((reinterpret_cast<uintptr_t>(g) & 7) == 0);
         if (rl < 3) {
-            for (int r = rl; r < UB_GR; r += 3) {
-                const int oy = oyb + r;
-                float2 v = make_float2(0.f, 0.f);
+            // all twelve loads of a thread are issued before the first store (the loop form waited for each
+            // load in turn: the kernel was bound by global-load latency, not bandwidth)
+            float2 v[UB_GR / 3];
+#pragma unroll
+            for (int k = 0; k < UB_GR / 3; ++k) {
+                const int oy = oyb + rl + 3 * k;
+                v[k] = make_float2(0.f, 0.f);
                 if (oy >= 0 && oy < Ho) {
                     const float *gp = g + (long)oy * Wo + ox;
                     if (pair_ok) {
-                        v = __ldg(reinterpret_cast<const float2 *>(gp));
+                        v[k] = __ldg(reinterpret_cast<const float2 *>(gp));
                     } else {
-                        if (ox >= 0 && ox < Wo) v.x = __ldg(gp);
-                        if (ox + 1 >= 0 && ox + 1 < Wo) v.y = __ldg(gp + 1);
+                        if (ox >= 0 && ox < Wo) v[k].x = __ldg(gp);
+                        if (ox + 1 >= 0 && ox + 1 < Wo) v[k].y = __ldg(gp + 1);
                     }
                 }
-                *reinterpret_cast<float2 *>(&s_g[r][2 * cp]) = v;
             }
+#pragma unroll
+            for (int k = 0; k < UB_GR / 3; ++k) *reinterpret_cast<float2 *>(&s_g[rl + 3 * k][2 * cp]) = v[k];
         }
     }
     __syncthreads();
