@@ -171,6 +171,25 @@ int unpool_add_forward_b200(const float *x, const float *res, float *out, long l
 int unpool_backward_b200(const float *grad_out, float *grad_x, long long N, int H, int W, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Reconstruction losses of the training step: MSELoss + GDL of a prediction
+ * against the ground truth in one pass, with the inverse transform v01 = (v + add) * mul folded in.
+ * replaces, per prediction tensor, src/environments/environments.py:363-371,447-451 (permute + contiguous +
+ * inverse_transform twice, torch.nn.MSELoss, GDL) and src/losses/losses.py:24-45 (sliced differences, two
+ * L1Loss(reduce=False), sliced copies, add, mean).  pred / target [planes,H,W] contiguous (any plane order:
+ * both results are means).  out2[0] = mean((x01-y01)^2), out2[1] = the GDL mean over planes*(H-1)*(W-1)
+ * (NaN when H == 1 or W == 1, like the mean of an empty tensor).  `workspace`: device scratch of
+ * l2_gdl_loss_workspace_bytes() bytes (per-CTA partial sums; the final sum is taken in a fixed order in
+ * double, so the result is deterministic).
+ * Backward: grad_pred = grad_mse * d mse/d pred + grad_gdl * d gdl/d pred, where grad_mse / grad_gdl are
+ * DEVICE scalars (the upstream gradients of the two means; NULL = 0), read on the device: no host sync.
+ * sign(0) = 0 as in torch's abs backward. */
+long long l2_gdl_loss_workspace_bytes(long long planes, int H, int W);
+int l2_gdl_loss_forward_b200(const float *pred, const float *target, long long planes, int H, int W, float add, float mul,
+                             float *out2, void *workspace, void *stream);
+int l2_gdl_loss_backward_b200(const float *pred, const float *target, long long planes, int H, int W, float add, float mul,
+                              const float *grad_mse, const float *grad_gdl, float *grad_pred, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helper: a pure FFMA loop, used by bench.py to report the on-box FP32 FMA
  * ceiling next to the nominal 148 x 128 x 2 x f_SM.  Writes one float per thread to `sink`
  * (gridDim*blockDim floats).  flops = 2 * 8 * iters * grid * block. */

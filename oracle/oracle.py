@@ -451,6 +451,54 @@ def upsample_bilinear2x_backward(g):
     return out
 
 
+# --------------------------------------------------------------------------------------------
+# reconstruction losses of the training step
+# --------------------------------------------------------------------------------------------
+
+def _gdl_args(x01, y01):
+    """The arguments of the two |.| terms of GDL (losses.py:30-35), evaluated in FP32 with one rounding per
+    reference operation so that their SIGNS (the integer part of the backward) are the reference's own."""
+    x = np.asarray(x01, np.float32)
+    y = np.asarray(y01, np.float32)
+    H, W = x.shape[-2:]
+    x = x.reshape(-1, H, W)
+    y = y.reshape(-1, H, W)
+    w_arg = ((x[:, :, :-1] - x[:, :, 1:]) - (y[:, :, :-1] - y[:, :, 1:]))[:, 1:, :]   # rows 1.., cols 0..W-2
+    h_arg = ((x[:, 1:, :] - x[:, :-1, :]) - (y[:, 1:, :] - y[:, :-1, :]))[:, :, 1:]   # rows 0..H-2, cols 1..
+    return x, y, w_arg, h_arg
+
+
+def l2_gdl_loss(pred, target, add=1.0, mul=0.5):
+    """(MSELoss, GDL) of the inverse-transformed tensors   (environments.py:363-371; util.py:22-23;
+    losses.py:24-45 with reduce=True).  Terms in FP32 like the reference, sums in float64."""
+    x01 = ((np.asarray(pred, np.float32) + np.float32(add)) * np.float32(mul)).astype(np.float32)
+    y01 = ((np.asarray(target, np.float32) + np.float32(add)) * np.float32(mul)).astype(np.float32)
+    x, y, w_arg, h_arg = _gdl_args(x01, y01)
+    d = (x - y).astype(np.float64)
+    mse = float(np.mean(d * d))
+    n_gdl = w_arg.size
+    gdl = float((np.abs(w_arg).astype(np.float64).sum() + np.abs(h_arg).astype(np.float64).sum()) / n_gdl) if n_gdl else float("nan")
+    return mse, gdl
+
+
+def l2_gdl_loss_backward(pred, target, g_mse, g_gdl, add=1.0, mul=0.5):
+    """d(g_mse * mse + g_gdl * gdl) / d pred; sign(0) = 0 as in torch's abs backward."""
+    shape = np.asarray(pred).shape
+    x01 = ((np.asarray(pred, np.float32) + np.float32(add)) * np.float32(mul)).astype(np.float32)
+    y01 = ((np.asarray(target, np.float32) + np.float32(add)) * np.float32(mul)).astype(np.float32)
+    x, y, w_arg, h_arg = _gdl_args(x01, y01)
+    g = 2.0 * g_mse * mul / x.size * (x - y).astype(np.float64)
+    if w_arg.size:
+        cg = g_gdl * mul / w_arg.size
+        sw = np.sign(w_arg).astype(np.float64)
+        sh = np.sign(h_arg).astype(np.float64)
+        g[:, 1:, :-1] += cg * sw     # + on the left column of the pair
+        g[:, 1:, 1:] -= cg * sw      # - on the right column
+        g[:, 1:, 1:] += cg * sh      # + on the lower row of the pair
+        g[:, :-1, 1:] -= cg * sh     # - on the upper row
+    return g.reshape(shape)
+
+
 def rel_err(x, ref):
     """max |x-ref| / max(|ref|, rms(ref)) -- the tolerance definition of SURVEY.md section 7
     (V/H are unnormalised and signed, so outputs have zero crossings)."""

@@ -179,3 +179,24 @@ def test_upsample_and_unpool_against_torch():
         assert np.array_equal(O.fixed_unpooling(x), ref)
     i0, i1, w0, w1 = O.upsample_bilinear2x_taps(16)
     assert i0[0] == 0 and i1[-1] == 15 and i0[-1] == 15 and abs(w0[-1] + w1[-1] - 1) < 1e-7
+
+
+def test_loss_oracle_matches_reference_gdl_golden():
+    """tests/golden/l2_gdl_ref.npz was produced by the reference's own GDL class + torch.nn.MSELoss
+    (tests/golden/make_loss_golden.py); the oracle must reproduce values and gradients, ties included."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "l2_gdl_ref.npz"))
+    for i in range(int(z["n"])):
+        x, y = z["x%d" % i], z["y%d" % i]
+        mse, gdl = O.l2_gdl_loss(x, y)
+        assert abs(mse - float(z["mse%d" % i])) <= 1e-6 * abs(mse)
+        assert abs(gdl - float(z["gdl%d" % i])) <= 1e-6 * abs(gdl)
+        g = O.l2_gdl_loss_backward(x, y, float(z["g_mse"]), float(z["g_gdl"]))
+        assert O.rel_err(z["grad%d" % i], g) < 1e-5
+    # the product's torch GDL module (CPU / API parity with losses.py:4-45) agrees as well
+    import torch
+    from video_frame_inpainting_b200.losses.losses import GDL
+    a = (torch.from_numpy(z["x0"]) + 1.) / 2
+    b = (torch.from_numpy(z["y0"]) + 1.) / 2
+    assert abs(GDL()(a, b).item() - float(z["gdl0"])) < 1e-6
+    assert GDL(reduce=False)(a, b).shape == a.shape[:-2] + (a.shape[-2] - 1, a.shape[-1] - 1)

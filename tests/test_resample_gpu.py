@@ -9,7 +9,10 @@ from tests.helpers import assert_close, to_cuda
 
 pytestmark = pytest.mark.gpu
 
-UP_SHAPES = [(2, 3, 5, 7), (1, 2, 1, 1), (1, 64, 16, 16), (2, 5, 3, 8), (1, 1, 33, 2), (4, 64, 64, 64)]
+UP_SHAPES = [(2, 3, 5, 7), (1, 2, 1, 1), (1, 64, 16, 16), (2, 5, 3, 8), (1, 1, 33, 2), (4, 64, 64, 64),
+             # adjoint kernel: W = 4 (both threads of a row use the shifted border window), odd H with several
+             # row blocks, a plane count that leaves the last CTA ragged, the UCF decoder shape
+             (3, 7, 9, 4), (1, 3, 37, 6), (2, 33, 21, 10), (1, 16, 120, 160), (2, 3, 1, 4), (1, 5, 2, 12)]
 
 
 @pytest.mark.parametrize("B,C,H,W", UP_SHAPES)

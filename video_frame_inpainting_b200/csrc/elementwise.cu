@@ -9,7 +9,12 @@ static inline unsigned stream_grid(long work_items, int block)
 {
     long g = (work_items + block - 1) / block;
     const long cap = (long)sm_count() * 8;  // 8 resident 256-thread CTAs per SM, grid-stride beyond
-    if (g > cap) g = cap;
+    if (g > cap) {
+        // every thread makes the same number of grid-stride trips (a grid of exactly `cap` CTAs leaves a ragged
+        // second trip: 2048 CTAs of work on 1184 slots ran as 1 + 0.73 waves)
+        const long trips = (g + cap - 1) / cap;
+        g = (g + trips - 1) / trips;
+    }
     if (g < 1) g = 1;
     return (unsigned)g;
 }
@@ -17,7 +22,39 @@ static inline unsigned stream_grid(long work_items, int block)
 // ------------------------------------------------------------------------------------------------
 // ConvLSTM gates (mcnet.py:287-293).  conv_out [B,4F,HW] holds (i,j,f,o) as four contiguous F*HW
 // slabs per sample; state [B,2F,HW] holds (c,h).  28 B of traffic per state element.
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+//
+// Activations: the accurate expf / tanhf / IEEE-division sequences cost ~170 instructions per state element,
+// which made the forward kernel ISSUE-bound (63 % of the copy bandwidth, same time as the backward kernel that
+// moves twice the bytes).  ex2.approx / rcp.approx based forms are ~3x shorter; their error (a few ulp of the
+// exponential, <= 2e-6 relative for |x| < 20) is far inside the 1e-4 parity bar.  tanh needs care near zero,
+// where (1 - t) / (1 + t) cancels: below 0.25 an odd polynomial (next term 9e-3 * x^11) is selected.
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 1 / (1 + e^-x): e^-x = +inf for x < -88.7 -> rcp(inf) = 0, the limit
+__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+
+__device__ __forceinline__ float tanh_acc(float x)
+{
+    const float ax = fabsf(x);
+    const float t = ex2_ftz(-2.8853900817779268f * ax);
+    const float big = (1.f - t) * rcp_ftz(1.f + t);
+    const float x2 = ax * ax;
+    float p = fmaf(x2, 62.f / 2835.f, -17.f / 315.f);
+    p = fmaf(x2, p, 2.f / 15.f);
+    p = fmaf(x2, p, -1.f / 3.f);
+    p = fmaf(x2 * ax, p, ax);
+    return copysignf(ax < 0.25f ? p : big, x);
+}
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -44,8 +81,8 @@ gates_fwd_kernel(const float *__restrict__ conv, const float *__restrict__ state
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            nc[k] = c[k] * sigmoid_acc(gf[k] + fb) + sigmoid_acc(gi[k]) * tanhf(gj[k]);
-            nh[k] = tanhf(nc[k]) * sigmoid_acc(go[k]);
+            nc[k] = c[k] * sigmoid_acc(gf[k] + fb) + sigmoid_acc(gi[k]) * tanh_acc(gj[k]);
+            nh[k] = tanh_acc(nc[k]) * sigmoid_acc(go[k]);
         }
         if (VEC == 4) {
             *reinterpret_cast<float4 *>(ob) = *reinterpret_cast<float4 *>(nc);
@@ -89,8 +126,8 @@ gates_bwd_kernel(const float *__restrict__ conv, const float *__restrict__ state
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             const float si = sigmoid_acc(gi[k]), sf = sigmoid_acc(gf[k] + fb), so = sigmoid_acc(go[k]);
-            const float tj = tanhf(gj[k]);
-            const float tc = tanhf(c[k] * sf + si * tj);
+            const float tj = tanh_acc(gj[k]);
+            const float tc = tanh_acc(c[k] * sf + si * tj);
             const float gct = gcn[k] + ghn[k] * so * (1.f - tc * tc);
             di[k] = gct * tj * si * (1.f - si);
             dj[k] = gct * si * (1.f - tj * tj);

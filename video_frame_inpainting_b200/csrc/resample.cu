@@ -9,6 +9,8 @@
 //     a clone().zero_(), two permutes and an add in the reference), forward and adjoint.
 //
 // All four are pure streaming kernels: the forward kernels are bound by the write of the 2H x 2W result.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tai {
@@ -145,106 +147,160 @@ __device__ __forceinline__ float up_adjoint_weight(int d, int i, float ratio, in
     return acc;
 }
 
-// Separable as well: a CTA owns a UB_TH x UB_TW tile of the INPUT gradient; it stages the output-gradient
-// rows 2*y0-2 .. 2*(y0+UB_TH-1)+3 and columns 2*x0-2 .. 2*(x0+UB_TW-1)+3 once (zero outside the image),
-// reduces them along x with the six column weights of each input column, then along y with the six row
-// weights of each input row.  (The direct form -- every thread loading its 6 x 6 neighbourhood -- issued 12
-// global loads per input element and ran at 23 % of the copy bandwidth.)
-constexpr int UB_TH = 16, UB_TW = 64, UB_NT = 256;
-constexpr int UB_GR = 2 * UB_TH + 4, UB_GC = 2 * UB_TW + 4;
+// Register sliding window, no shared-memory staging: a thread owns the input-gradient columns (x, x+1), x even,
+// of one plane and walks R input rows downwards.  For every output-gradient row d it loads eight consecutive
+// columns starting at cb = clamp(2x-2, 0, 2W-8) (four 64-bit loads off ONE row pointer with immediate offsets;
+// the neighbouring threads' overlap is served by L1), reduces them along x with two sets of eight column
+// weights (registers, formed once from the columns' real indices, so the shifted window of the two border
+// threads needs no special case and no load is ever out of bounds) and keeps the values of the six rows
+// 2y-2 .. 2y+3 in a register window that slides by two rows per input row; the six row weights of an input row
+// are the same for the whole CTA and come from a small shared-memory table (broadcast reads).
+// Per input element: 4 LDG.64, 22 FMAs, half a 64-bit store -- the separable shared-memory version (stage,
+// reduce along x, reduce along y: ~20 shared/global instructions per input element, two barriers per tile) ran
+// at 23-45 % of the copy bandwidth, bound by LSU issue.  Deterministic (a gather, no atomics).
+constexpr int UA_NT = 256, UA_RMAX = 32;
 
-__global__ void __launch_bounds__(UB_NT)
-upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, int H, int W, float rh, float rw,
-                      int tiles_y, int tiles_x)
+// rows outside the image are read from a clamped address and replaced by zeros afterwards (a select, so that
+// an Inf in the border row cannot turn into 0 * Inf); no branches: every load of a step is in flight before
+// the first use
+__device__ __forceinline__ void up_adj_load_row(const float *__restrict__ pc, int d, int Ho, int Wo, float2 (&v)[4])
 {
-    __shared__ __align__(8) float s_g[UB_GR][UB_GC + 2];  // even pitch: 64-bit reads of column pairs
-    __shared__ float s_t[UB_GR][UB_TW + 8];                // rows 2 apart land in different bank halves
-    __shared__ __align__(16) float s_w[UB_TW + UB_TH][8];  // six adjoint weights per input column, then per input row
-    const int Ho = 2 * H, Wo = 2 * W;
-    int t = blockIdx.x;
-    const int tx = t % tiles_x;
-    t /= tiles_x;
-    const int ty = t % tiles_y;
-    const long n = t / tiles_y;
-    const int y0 = ty * UB_TH, x0 = tx * UB_TW;
-    const int oyb = 2 * y0 - 2, oxb = 2 * x0 - 2;
-    const float *g = gout + n * Ho * Wo;
-    for (int i = threadIdx.x; i < (UB_TW + UB_TH) * 6; i += UB_NT) {  // weights: formed once per CTA
+    const float2 *rp = reinterpret_cast<const float2 *>(pc + min(max(d, 0), Ho - 1) * Wo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(rp + k);
+}
+
+__device__ __forceinline__ void up_adj_reduce_x(const float2 (&v)[4], const float (&wx0)[8], const float (&wx1)[8], bool rok,
+                                                float &t0, float &t1)
+{
+    float a = wx0[0] * v[0].x, b = wx1[0] * v[0].x;
+    a = fmaf(wx0[1], v[0].y, a); b = fmaf(wx1[1], v[0].y, b);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        a = fmaf(wx0[2 * k], v[k].x, a); b = fmaf(wx1[2 * k], v[k].x, b);
+        a = fmaf(wx0[2 * k + 1], v[k].y, a); b = fmaf(wx1[2 * k + 1], v[k].y, b);
+    }
+    t0 = rok ? a : 0.f;
+    t1 = rok ? b : 0.f;
+}
+
+// needs W even, W >= 4 and 8 B-aligned tensors
+template <bool PIPE>
+__global__ void __launch_bounds__(UA_NT)
+upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, long planes, int H, int W, float rh, float rw,
+                      int R)
+{
+    __shared__ __align__(16) float s_wy[UA_RMAX][8];
+    const int Ho = 2 * H, Wo = 2 * W, wp = W / 2;
+    const int y_begin = blockIdx.y * R;
+    for (int i = threadIdx.x; i < R * 6; i += UA_NT) {  // row weights of this CTA's R input rows
         const int e = i / 6, k = i - e * 6;
-        float w;
-        if (e < UB_TW) {
-            const int x = x0 + e;
-            w = (x < W) ? up_adjoint_weight(2 * x - 2 + k, x, rw, W, Wo) : 0.f;
+        const int y = y_begin + e;
+        s_wy[e][k] = (y < H) ? up_adjoint_weight(2 * y - 2 + k, y, rh, H, Ho) : 0.f;
+    }
+    __syncthreads();
+    const long item = (long)blockIdx.x * UA_NT + threadIdx.x;
+    if (item >= planes * wp) return;
+    const long n = item / wp;
+    const int x = 2 * (int)(item - n * wp);
+    const int cb = min(max(2 * x - 2, 0), Wo - 8);
+    float wx0[8], wx1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        wx0[k] = up_adjoint_weight(cb + k, x, rw, W, Wo);
+        wx1[k] = up_adjoint_weight(cb + k, x + 1, rw, W, Wo);
+    }
+    const float *pc = gout + n * Ho * Wo + cb;
+    float *o = gin + n * H * W + x;
+
+    float a0[4], a1[4];  // x-reduced rows 2y-2 .. 2y+1 of the current input row y
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int d = 2 * y_begin - 2 + r;
+        float2 v[4];
+        up_adj_load_row(pc, d, Ho, Wo, v);
+        up_adj_reduce_x(v, wx0, wx1, d >= 0 && d < Ho, a0[r], a1[r]);
+    }
+    const int y_end = min(H, y_begin + R);
+    // two input rows per step = four new gradient rows.  Software-pipelined: the sixteen loads of step s+1 are
+    // issued before the arithmetic of step s, so a warp always has 2 KB of loads in flight.
+    float2 v[4][4];
+    if (PIPE) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y_begin + 2 + r, Ho, Wo, v[r]);
+    }
+#pragma unroll 1
+    for (int y = y_begin; y < y_end; y += 2) {
+        float2 vn[4][4];
+        if (PIPE) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y + 6 + r, Ho, Wo, vn[r]);  // clamped: never out of bounds
         } else {
-            const int y = y0 + e - UB_TW;
-            w = (y < H) ? up_adjoint_weight(2 * y - 2 + k, y, rh, H, Ho) : 0.f;
-        }
-        s_w[e][k] = w;
-    }
-    {   // stage: 66 column PAIRS per row (64-bit loads when the pair is inside the image), 3 rows at a time
-        const int cp = threadIdx.x % 66, rl = threadIdx.x / 66;  // rl == 3 for the last 58 threads: idle
-        const int ox = oxb + 2 * cp;
-        const bool pair_ok = (Wo % 2 == 0) && ox >= 0 && ox + 1 < Wo && ((reinterpret_cast<uintptr_t>(g) & 7) == 0);
-        if (rl < 3) {
-            // all twelve loads of a thread are issued before the first store (the loop form waited for each
-            // load in turn: the kernel was bound by global-load latency, not bandwidth)
-            float2 v[UB_GR / 3];
 #pragma unroll
-            for (int k = 0; k < UB_GR / 3; ++k) {
-                const int oy = oyb + rl + 3 * k;
-                v[k] = make_float2(0.f, 0.f);
-                if (oy >= 0 && oy < Ho) {
-                    const float *gp = g + (long)oy * Wo + ox;
-                    if (pair_ok) {
-                        v[k] = __ldg(reinterpret_cast<const float2 *>(gp));
-                    } else {
-                        if (ox >= 0 && ox < Wo) v[k].x = __ldg(gp);
-                        if (ox + 1 >= 0 && ox + 1 < Wo) v[k].y = __ldg(gp + 1);
-                    }
-                }
+            for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y + 2 + r, Ho, Wo, v[r]);
+        }
+        float t0[4], t1[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) up_adj_reduce_x(v[r], wx0, wx1, 2 * y + 2 + r < Ho, t0[r], t1[r]);
+        const float4 wa = *reinterpret_cast<const float4 *>(&s_wy[y - y_begin][0]);
+        const float2 wb = *reinterpret_cast<const float2 *>(&s_wy[y - y_begin][4]);
+        const float4 wc = *reinterpret_cast<const float4 *>(&s_wy[y - y_begin + 1][0]);
+        const float2 wd = *reinterpret_cast<const float2 *>(&s_wy[y - y_begin + 1][4]);
+        float p0 = wa.x * a0[0], p1 = wa.x * a1[0];
+        p0 = fmaf(wa.y, a0[1], p0); p1 = fmaf(wa.y, a1[1], p1);
+        p0 = fmaf(wa.z, a0[2], p0); p1 = fmaf(wa.z, a1[2], p1);
+        p0 = fmaf(wa.w, a0[3], p0); p1 = fmaf(wa.w, a1[3], p1);
+        p0 = fmaf(wb.x, t0[0], p0); p1 = fmaf(wb.x, t1[0], p1);
+        p0 = fmaf(wb.y, t0[1], p0); p1 = fmaf(wb.y, t1[1], p1);
+        float q0 = wc.x * a0[2], q1 = wc.x * a1[2];
+        q0 = fmaf(wc.y, a0[3], q0); q1 = fmaf(wc.y, a1[3], q1);
+        q0 = fmaf(wc.z, t0[0], q0); q1 = fmaf(wc.z, t1[0], q1);
+        q0 = fmaf(wc.w, t0[1], q0); q1 = fmaf(wc.w, t1[1], q1);
+        q0 = fmaf(wd.x, t0[2], q0); q1 = fmaf(wd.x, t1[2], q1);
+        q0 = fmaf(wd.y, t0[3], q0); q1 = fmaf(wd.y, t1[3], q1);
+        float *oy = o + y * W;
+        *reinterpret_cast<float2 *>(oy) = make_float2(p0, p1);
+        if (y + 1 < y_end) *reinterpret_cast<float2 *>(oy + W) = make_float2(q0, q1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            a0[r] = t0[r];
+            a1[r] = t1[r];
+        }
+        if (PIPE) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[r][k] = vn[r][k];
+        }
+    }
+}
+
+// Any shape / alignment (odd W, W < 4, unaligned views): one thread per input element gathers its 6 x 6
+// neighbourhood directly.  Not a performance path.
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_generic_kernel(const float *__restrict__ gout, float *__restrict__ gin, long total, int H, int W, float rh,
+                              float rw)
+{
+    const int Ho = 2 * H, Wo = 2 * W;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        const long row = idx / W;
+        const int y = (int)(row % H);
+        const float *g = gout + (row / H) * Ho * Wo;
+        float acc = 0.f;
+        for (int i = 0; i < 6; ++i) {
+            const int d = 2 * y - 2 + i;
+            const float wy = up_adjoint_weight(d, y, rh, H, Ho);
+            if (wy == 0.f) continue;
+            float t = 0.f;
+            for (int k = 0; k < 6; ++k) {
+                const int e = 2 * x - 2 + k;
+                const float wx = up_adjoint_weight(e, x, rw, W, Wo);
+                if (wx != 0.f) t = fmaf(wx, g[(long)d * Wo + e], t);
             }
-#pragma unroll
-            for (int k = 0; k < UB_GR / 3; ++k) *reinterpret_cast<float2 *>(&s_g[rl + 3 * k][2 * cp]) = v[k];
+            acc = fmaf(wy, t, acc);
         }
-    }
-    __syncthreads();
-    {   // along x: thread = one input column, six weights in registers, loops over the staged rows
-        const int xl = threadIdx.x % UB_TW;
-        const float4 wa = *reinterpret_cast<const float4 *>(&s_w[xl][0]);
-        const float2 wb = *reinterpret_cast<const float2 *>(&s_w[xl][4]);
-#pragma unroll 3
-        for (int r = threadIdx.x / UB_TW; r < UB_GR; r += UB_NT / UB_TW) {
-            const float2 *gp = reinterpret_cast<const float2 *>(&s_g[r][2 * xl]);
-            const float2 g0 = gp[0], g1 = gp[1], g2 = gp[2];
-            float acc = wa.x * g0.x;
-            acc = fmaf(wa.y, g0.y, acc);
-            acc = fmaf(wa.z, g1.x, acc);
-            acc = fmaf(wa.w, g1.y, acc);
-            acc = fmaf(wb.x, g2.x, acc);
-            acc = fmaf(wb.y, g2.y, acc);
-            s_t[r][xl] = acc;
-        }
-    }
-    __syncthreads();
-    {   // along y: thread = one input row (six weights in registers), loops over the columns
-        const int yl = threadIdx.x / (UB_NT / UB_TH);            // 16 threads per input row
-        const int y = y0 + yl;
-        if (y < H) {
-            const float4 wa = *reinterpret_cast<const float4 *>(&s_w[UB_TW + yl][0]);
-            const float2 wb = *reinterpret_cast<const float2 *>(&s_w[UB_TW + yl][4]);
-            float *orow = gin + (n * H + y) * W;
-#pragma unroll
-            for (int k = 0; k < UB_TW / (UB_NT / UB_TH); ++k) {
-                const int xl = (threadIdx.x % (UB_NT / UB_TH)) + k * (UB_NT / UB_TH);
-                float acc = wa.x * s_t[2 * yl][xl];
-                acc = fmaf(wa.y, s_t[2 * yl + 1][xl], acc);
-                acc = fmaf(wa.z, s_t[2 * yl + 2][xl], acc);
-                acc = fmaf(wa.w, s_t[2 * yl + 3][xl], acc);
-                acc = fmaf(wb.x, s_t[2 * yl + 4][xl], acc);
-                acc = fmaf(wb.y, s_t[2 * yl + 5][xl], acc);
-                if (x0 + xl < W) orow[x0 + xl] = acc;
-            }
-        }
+        gin[idx] = acc;
     }
 }
 
@@ -343,11 +399,24 @@ extern "C" int upsample_bilinear2x_backward_b200(const float *grad_out, float *g
     cudaStream_t st = (cudaStream_t)stream;
     const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
     const long in_el = (long)N * H * W;
-    const int tiles_y = ceil_div(H, UB_TH), tiles_x = ceil_div(W, UB_TW);
-    const long long blocks = N * tiles_y * tiles_x;
-    TAI_REQUIRE(blocks < (1LL << 31), TAI_ERR_TOO_LARGE, "upsample_bilinear2x_backward_b200: too many tiles");
     TimingScope ts("upsample2x_bwd", st, 0.0, 4.0 * (5 * in_el));  // read the 2H x 2W gradient once, write H x W
-    upsample2x_bwd_kernel<<<(unsigned)blocks, UB_NT, 0, st>>>(grad_out, grad_in, H, W, rh, rw, tiles_y, tiles_x);
+    if ((W % 2) == 0 && W >= 4 && (((uintptr_t)grad_out | (uintptr_t)grad_in) & 7) == 0) {
+        const long planes = (long)N;
+        const int wp = W / 2;
+        int R = 16;  // input rows per thread (even); shorter walks when the tensor would not fill the chip
+        while (R > 4 && planes * wp * ceil_div(H, R) < (long)sm_count() * 1024) R /= 2;
+        const long long bx = (planes * wp + UA_NT - 1) / UA_NT;
+        TAI_REQUIRE(bx < (1LL << 31) && ceil_div(H, R) < 65536, TAI_ERR_TOO_LARGE,
+                    "upsample_bilinear2x_backward_b200: grid too large");
+        const dim3 grid((unsigned)bx, (unsigned)ceil_div(H, R));
+        static const int variant = getenv("TAI_UPADJ_VARIANT") ? atoi(getenv("TAI_UPADJ_VARIANT")) : 1;
+        if (variant == 1)
+            upsample2x_bwd_kernel<true><<<grid, UA_NT, 0, st>>>(grad_out, grad_in, planes, H, W, rh, rw, R);
+        else
+            upsample2x_bwd_kernel<false><<<grid, UA_NT, 0, st>>>(grad_out, grad_in, planes, H, W, rh, rw, R);
+    } else {
+        upsample2x_bwd_generic_kernel<<<resample_grid(in_el, 256), 256, 0, st>>>(grad_out, grad_in, in_el, H, W, rh, rw);
+    }
     return check_launch("upsample2x_bwd_kernel");
 }
 

@@ -10,7 +10,8 @@ names, loss composition and checkpoint dictionary.  Differences, all on the host
 * gradients live in one flat buffer per network and are all-reduced bucket by bucket while backward is
   still running (``parallel.FlatGradAllReducer``) when the process group has more than one rank -- the
   reference is single-GPU;
-* nothing here launches a custom kernel directly: the kernels are reached through
+* the reconstruction losses (MSELoss + GDL on the inverse-transformed frames, three prediction tensors per
+  step) go through the fused loss kernels (``losses.L2GDLLoss``); every other kernel is reached through
   ``generator(T, preceding, following)``.
 """
 import os
@@ -19,7 +20,7 @@ import numpy as np
 import torch
 
 from ..discriminators.SNDiscriminator import SNDiscriminator
-from ..losses.losses import GDL
+from ..losses.losses import GDL, L2GDLLoss
 from ..parallel import FlatGradAllReducer, broadcast_module
 from ..util.util import inverse_transform, move_to_devices, weights_init
 
@@ -186,6 +187,7 @@ class L2GDLDiscTrainingEnvironment(BaseTrainingEnvironment):
                                                            max_T, max_F, padding_size)
         self.loss_Lp = torch.nn.MSELoss()
         self.loss_gdl = GDL()
+        self.loss_Lp_gdl = L2GDLLoss()   # both of the above in one kernel pass (used by compute_loss_G)
         self.loss_d = torch.nn.BCEWithLogitsLoss()
         self.alpha, self.beta = alpha, beta
         self.disc_t = disc_t
@@ -249,10 +251,8 @@ class L2GDLDiscTrainingEnvironment(BaseTrainingEnvironment):
 
     def compute_loss_G(self):
         super(L2GDLDiscTrainingEnvironment, self).compute_loss_G()
-        gt = self._time_major01(self.gt_middle_frames)
-        outputs = self._time_major01(self.gen_output['pred'])
-        self.Lp = self.loss_Lp(outputs, gt)
-        self.gdl = self.loss_gdl(outputs, gt)
+        # environments.py:363-371: time-major regrouping + inverse_transform + MSELoss + GDL, fused
+        self.Lp, self.gdl = self.loss_Lp_gdl(self.gen_output['pred'], self.gt_middle_frames)
         h = self.discriminator(self._video(self.gen_output['pred']))
         self.L_GAN = self.loss_d(h, torch.ones_like(h))
         self.loss_G = self.loss_G + self.alpha * (self.Lp + self.gdl) + self.beta * self.L_GAN
@@ -280,13 +280,9 @@ class TAITrainingEnvironment(L2GDLDiscTrainingEnvironment):
 
     def compute_loss_G(self):
         super(TAITrainingEnvironment, self).compute_loss_G()
-        gt = self._time_major01(self.gt_middle_frames)
-        fwd = self._time_major01(self.gen_output['pred_forward'])
-        bwd = self._time_major01(self.gen_output['pred_backward'])
-        self.Lp_forward = self.loss_Lp(fwd, gt)
-        self.Lp_backward = self.loss_Lp(bwd, gt)
-        self.gdl_forward = self.loss_gdl(fwd, gt)
-        self.gdl_backward = self.loss_gdl(bwd, gt)
+        # environments.py:437-451
+        self.Lp_forward, self.gdl_forward = self.loss_Lp_gdl(self.gen_output['pred_forward'], self.gt_middle_frames)
+        self.Lp_backward, self.gdl_backward = self.loss_Lp_gdl(self.gen_output['pred_backward'], self.gt_middle_frames)
         self.loss_G = self.loss_G + self.alpha * (self.Lp_forward + self.Lp_backward + self.gdl_forward
                                                   + self.gdl_backward)
 

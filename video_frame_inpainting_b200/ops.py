@@ -369,6 +369,66 @@ def slomo_refine_blend(i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, t):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# reconstruction losses (MSELoss + GDL in one pass)
+# ------------------------------------------------------------------------------------------------
+
+def l2_gdl_loss_forward(pred, target, add=1.0, mul=0.5):
+    """(mse, gdl) of v01 = (v + add) * mul as a 2-element tensor   (environments.py:363-371; losses.py:24-45)."""
+    dev = _check("l2_gdl_loss_forward", pred, target)
+    assert pred.shape == target.shape and pred.dim() >= 2
+    H, W = pred.shape[-2:]
+    planes = pred.numel() // (H * W)
+    with torch.cuda.device(dev):
+        out = torch.empty(2, device=dev, dtype=torch.float32)
+        nbytes = int(_lib.load().l2_gdl_loss_workspace_bytes(planes, H, W))
+        ws = torch.empty(max(nbytes, 8) // 4, device=dev, dtype=torch.float32)
+        _lib.call("l2_gdl_loss_forward_b200", _ptr(pred), _ptr(target), planes, H, W, float(add), float(mul),
+                  _ptr(out), _ptr(ws), _stream())
+    return out
+
+
+def l2_gdl_loss_backward(pred, target, grad_mse, grad_gdl, add=1.0, mul=0.5):
+    """grad_mse / grad_gdl: 1-element CUDA tensors (or None) -- read on the device."""
+    dev = _check("l2_gdl_loss_backward", pred, target, grad_mse, grad_gdl)
+    H, W = pred.shape[-2:]
+    planes = pred.numel() // (H * W)
+    with torch.cuda.device(dev):
+        g = torch.empty_like(pred)
+        _lib.call("l2_gdl_loss_backward_b200", _ptr(pred), _ptr(target), planes, H, W, float(add), float(mul),
+                  _ptr(grad_mse), _ptr(grad_gdl), _ptr(g), _stream())
+    return g
+
+
+class L2GDLLossFunction(torch.autograd.Function):
+    """(pred, target) -> (mse, gdl), both 0-dim.  The target is treated as a constant, as in the training
+    step (ground-truth frames).  Backward recomputes the terms from pred / target: nothing but the two
+    input tensors is kept."""
+
+    @staticmethod
+    def forward(ctx, pred, target, add, mul):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        out = l2_gdl_loss_forward(pred, target, add, mul)
+        ctx.save_for_backward(pred, target)
+        ctx.affine = (add, mul)
+        return out[0], out[1]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_mse, g_gdl):
+        pred, target = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        g_mse = g_mse.reshape(1).contiguous() if g_mse is not None else None
+        g_gdl = g_gdl.reshape(1).contiguous() if g_gdl is not None else None
+        return l2_gdl_loss_backward(pred, target, g_mse, g_gdl, *ctx.affine), None, None, None
+
+
+def l2_gdl_loss(pred, target, add=1.0, mul=0.5):
+    return L2GDLLossFunction.apply(pred, target, add, mul)
+
+
 def ffma_probe(grid, block, iters, packed=False):
     """Launch the pure-FFMA probe kernel; returns the sink tensor (flops = 2*8*iters*grid*block)."""
     sink = torch.empty(grid * block, device="cuda", dtype=torch.float32)
