@@ -101,7 +101,7 @@ def test_grad_input_tap_count_bit_exact(cuda, Ho, Wo, ks):
     assert table.sum() == Ho * Wo * ks * ks  # every tap of every output pixel lands exactly once
 
 
-@pytest.mark.parametrize("H,W,p", [(16, 32, 25), (5, 7, 2), (1, 1, 3), (9, 4, 0)])
+@pytest.mark.parametrize("H,W,p", [(16, 32, 25), (5, 7, 2), (1, 1, 3), (9, 4, 0), (2, 6, 25), (3, 300, 4), (1, 40, 7)])
 def test_replication_pad_index_bit_exact(cuda, H, W, p):
     """Clamp logic of ReplicationPad2d (tai.py:170-171): padding an index image must reproduce the
     oracle's integer tables exactly; the adjoint of a ones image must give the integer multiplicity."""
@@ -114,6 +114,18 @@ def test_replication_pad_index_bit_exact(cuda, H, W, p):
     mult = ops.replication_pad_backward(torch.ones(1, 1, H + 2 * p, W + 2 * p, device="cuda"), p).cpu().numpy()
     ref = O.replication_pad_adjoint(np.ones((1, 1, H + 2 * p, W + 2 * p)), p)
     assert np.array_equal(mult, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("N,H,W,p", [(6, 16, 32, 25), (3, 2, 5, 3), (4, 1, 9, 2), (32, 128, 128, 25), (2, 7, 270, 6)])
+def test_replication_pad_adjoint_values(cuda, N, H, W, p):
+    """Random gradients, several images: border-row CTAs and interior-row warps of the adjoint kernel."""
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(9)
+    g = rng.normal(size=(N, 1, H + 2 * p, W + 2 * p)).astype(np.float32)
+    (tg,) = to_cuda(g)
+    out = ops.replication_pad_backward(tg, p).cpu().numpy()
+    assert_close(out, O.replication_pad_adjoint(g, p), what="pad adjoint")
+    assert np.array_equal(out, ops.replication_pad_backward(tg, p).cpu().numpy()), "deterministic"
 
 
 @pytest.mark.parametrize("B,C,H,W,ks,a,b", [
@@ -145,7 +157,12 @@ def test_fused_pad_sepconv_blend(cuda, B, C, H, W, ks, a, b):
     assert np.array_equal(pred_only.cpu().numpy(), pred.cpu().numpy())
 
 
-@pytest.mark.parametrize("B,C,H,W,ks", [(1, 1, 16, 32, 51), (2, 3, 12, 36, 13), (1, 1, 5, 7, 5), (2, 1, 32, 64, 13)])
+@pytest.mark.parametrize("B,C,H,W,ks", [
+    (1, 1, 16, 32, 51), (2, 3, 12, 36, 13), (1, 1, 5, 7, 5), (2, 1, 32, 64, 13),
+    # several tile columns (interior tiles + both borders), tiles that touch both borders at once, ragged
+    # sizes, three channels, ks = 25 / 37; H = 1 / 2: every row of the pad adjoint is a border row
+    (1, 1, 40, 128, 51), (1, 3, 24, 100, 51), (2, 1, 9, 20, 25), (1, 3, 17, 76, 37), (1, 1, 70, 36, 13),
+    (2, 1, 1, 12, 5), (1, 2, 2, 9, 13)])
 def test_fused_backward(cuda, B, C, H, W, ks):
     import torch
     from video_frame_inpainting_b200 import ops
@@ -169,6 +186,28 @@ def test_fused_backward(cuda, B, C, H, W, ks):
         assert_close(t[3 + 2 * s].grad.cpu().numpy(), O.sepconv_grad_horizontal(gD, padded, v, ks), tol=2 * TOL, what="fused gH%d" % s)
         gi = O.replication_pad_adjoint(O.sepconv_grad_input(gD, v, h, ks), p)
         assert_close(t[s].grad.cpu().numpy(), gi, tol=2 * TOL, what="fused gPred%d" % s)
+
+
+def test_fused_backward_full_size_adjoint_identity(cuda):
+    """BASELINE config B size through the fused operator: <g, blend(pf, pb)> == <g_pf, pf> + <g_pb, pb>
+    (the operator is linear in the two predictions; checks gI scatter + pad adjoint at 128 x 128, B = 32)."""
+    import torch
+    from video_frame_inpainting_b200 import ops
+    B, C, H, W, ks = 32, 1, 128, 128, 51
+    g = torch.Generator(device="cuda").manual_seed(1)
+    U = lambda *s: torch.rand(*s, device="cuda", generator=g) * 2 - 1
+    pf, pb = U(B, C, H, W).requires_grad_(), U(B, C, H, W).requires_grad_()
+    maps = [U(B, ks, H, W) / ks ** 0.5 for _ in range(4)]
+    pred, _, _ = ops.tai_blend_sepconv(pf, pb, *maps, ks, 0.5, 0.5)
+    go = U(B, C, H, W)
+    (pred * go).sum().backward()
+    dot = lambda x, y: (x.double() * y.double()).sum().item()
+    lhs, rhs = dot(go, pred.detach()), dot(pf.grad, pf.detach()) + dot(pb.grad, pb.detach())
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs)) + 1e-3, (lhs, rhs)
+    # one sample against the oracle
+    gi = O.replication_pad_adjoint(O.sepconv_grad_input(0.5 * go[3:4].cpu().numpy(), maps[0][3:4].cpu().numpy(),
+                                                        maps[1][3:4].cpu().numpy(), ks), ks // 2)
+    assert_close(pf.grad[3:4].cpu().numpy(), gi, tol=2 * TOL, what="full-size fused gPred")
 
 
 def test_full_size_properties_kth_batch(cuda):

@@ -58,6 +58,15 @@ def main():
         print(json.dumps({"case": "ffma_probe", "packed": packed, "tflops": fl / best / 1e12,
                           "frac_nominal": fl / best / PEAK_FMA}), flush=True)
 
+    if "copy" in args.cases.split(","):
+        # what a plain device-to-device copy reaches at the traffic volumes of the streaming kernels (the
+        # MEASURED_PEAKS.json figure is a large-buffer number): total traffic = 2 x buffer size
+        for mb in (16, 32, 64, 128, 256, 512, 2048):
+            n = mb * 1024 * 1024 // 8   # floats per buffer: traffic (read + write) = mb MB
+            src, dst = torch.randn(n, device=dev), torch.empty(n, device=dev)
+            med, best = timeit(lambda: dst.copy_(src), iters=args.iters, warm=args.warm, flush=flush)
+            print(json.dumps({"case": "copy", "traffic_mb": mb, "us_med": med * 1e6, "gbs": mb * 1048576 / med / 1e9,
+                              "frac_hbm_6553": mb * 1048576 / med / 6553e9}), flush=True)
     if "resample" in args.cases.split(","):
         for (B, C, H, W) in [(32, 64, 64, 64), (32, 128, 32, 32), (32, 32, 64, 64), (8, 64, 120, 160)]:
             x, res, gr = U(B, C, H, W), U(B, C, 2 * H, 2 * W), U(B, C, 2 * H, 2 * W)
@@ -72,7 +81,30 @@ def main():
                 med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
                 print(json.dumps({"case": "resample", "shape": [B, C, H, W], "kernel": k, "ms_med": med * 1e3,
                                   "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
-    for name in [c for c in args.cases.split(",") if c != "resample"]:
+    if "stream" in args.cases.split(","):
+        # ConvLSTM gates at the KTH training shape (B=32, 256 features, 16x16) and the UCF inference shape,
+        # fused MSE + GDL loss at the KTH training shape ([B*T, 1, 128, 128])
+        for (B, F, H, W) in [(32, 256, 16, 16), (8, 256, 30, 40)]:
+            conv, state, gns = torch.randn(B, 4 * F, H, W, device=dev), torch.randn(B, 2 * F, H, W, device=dev), \
+                torch.randn(B, 2 * F, H, W, device=dev)
+            el = B * F * H * W
+            runs = {"gates_fwd": (lambda: ops.convlstm_gates_forward(conv, state, 1.0), 28.0 * el),
+                    "gates_bwd": (lambda: ops.convlstm_gates_backward(conv, state, gns, 1.0), 52.0 * el)}
+            for k, (fn, by) in runs.items():
+                med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
+                print(json.dumps({"case": "stream", "shape": [B, F, H, W], "kernel": k, "ms_med": med * 1e3,
+                                  "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
+        for shape in [(32, 5, 1, 128, 128), (8, 3, 3, 240, 320)]:
+            x, y = U(*shape), U(*shape)
+            one = torch.ones(1, device=dev)
+            el = x.numel()
+            runs = {"l2_gdl_fwd": (lambda: ops.l2_gdl_loss_forward(x, y), 8.0 * el),
+                    "l2_gdl_bwd": (lambda: ops.l2_gdl_loss_backward(x, y, one, one), 12.0 * el)}
+            for k, (fn, by) in runs.items():
+                med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
+                print(json.dumps({"case": "stream", "shape": list(shape), "kernel": k, "ms_med": med * 1e3,
+                                  "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
+    for name in [c for c in args.cases.split(",") if c not in ("resample", "stream", "copy")]:
         B, C, Ho, Wo, ks = cases[name]
         I = U(B, C, Ho + ks - 1, Wo + ks - 1)
         P1, P2 = U(B, C, Ho, Wo), U(B, C, Ho, Wo)

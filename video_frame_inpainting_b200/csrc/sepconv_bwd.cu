@@ -281,50 +281,92 @@ __global__ void reppad_fwd_kernel(const float *__restrict__ in, float *__restric
 }
 
 // Adjoint: every unpadded element sums the padded elements that were copied from it (fixed order,
-// deterministic -- no atomics).  One warp per unpadded row: the lanes sum the source rows column by column
-// (coalesced; one source row for an interior output row, pad+1 for the first / last one), interior columns
-// are stored directly and the pad+1 columns of each border are combined with a shuffle tree.  (A thread per
-// output element leaves the four corner threads with (pad+1)^2 serial loads: 51 us for 4 MB at pad = 25.)
+// deterministic -- no atomics).  A group of threads owns one unpadded row: the threads sum the source rows
+// column by column (coalesced; one source row for an interior output row, pad+1 for the first / last one),
+// interior columns are stored directly and the pad+1 columns of each border are combined with a shuffle
+// tree.  Interior rows: one WARP per row.  The first / last row of every image: one whole CTA per row, the
+// pad+1 source rows unrolled so that eight loads per thread are in flight -- with a warp per row these two
+// rows (26 x 178 elements at pad = 25) were a serial chain of ~150 dependent-latency loads and set the
+// kernel's duration (35 us for 4 MB; a thread per output element: 51 us).
+template <int GROUP>
+__device__ __forceinline__ void reppad_bwd_row(const float *__restrict__ gpad, float *__restrict__ gin, long row, int H, int W,
+                                               int pad, int t, float *s_red)
+{
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int y = (int)(row % H);
+    const long img = row / H;
+    const int ylo = (y == 0) ? 0 : y + pad;
+    const int yhi = (y == H - 1) ? Hp - 1 : y + pad;
+    const float *src = gpad + (img * Hp + ylo) * Wp;
+    float *dst = gin + row * W;
+    float left = 0.f, right = 0.f;
+    for (int xx = t; xx < Wp; xx += GROUP) {
+        float cs = 0.f;
+#pragma unroll 8
+        for (int yy = 0; yy <= yhi - ylo; ++yy) cs += __ldg(src + (long)yy * Wp + xx);
+        const int x = xx - pad;
+        if (x <= 0)
+            left += cs;            // padded columns 0 .. pad feed output column 0
+        else if (x >= W - 1)
+            right += cs;           // padded columns W-1+pad .. Wp-1 feed output column W-1
+        else
+            dst[x] = cs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        left += __shfl_xor_sync(0xffffffffu, left, o);
+        right += __shfl_xor_sync(0xffffffffu, right, o);
+    }
+    if (GROUP > 32) {  // fixed-order sum of the warps' partials
+        const int w = t >> 5;
+        if ((t & 31) == 0) {
+            s_red[2 * w] = left;
+            s_red[2 * w + 1] = right;
+        }
+        __syncthreads();
+        left = right = 0.f;
+        for (int k = 0; k < GROUP / 32; ++k) {
+            left += s_red[2 * k];
+            right += s_red[2 * k + 1];
+        }
+    }
+    if (t == 0) {
+        if (W == 1) {
+            dst[0] = left + right;
+        } else {
+            dst[0] = left;
+            dst[W - 1] = right;
+        }
+    }
+}
+
+// grid: first the border-row CTAs (2 per image; 1 if H <= 2 rows are all border rows: handled by `nb`), then
+// the interior rows, 8 per CTA
 __global__ void __launch_bounds__(256)
 reppad_bwd_kernel(const float *__restrict__ gpad, float *__restrict__ gin, int N, int H, int W, int pad)
 {
-    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-    const int lane = threadIdx.x & 31;
-    const long nrows = (long)N * H;
-    for (long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows;
-         row += (long)gridDim.x * (blockDim.x >> 5)) {
-        const int y = (int)(row % H);
-        const long img = row / H;
-        const int ylo = (y == 0) ? 0 : y + pad;
-        const int yhi = (y == H - 1) ? Hp - 1 : y + pad;
-        const float *src = gpad + (img * Hp + ylo) * Wp;
-        float *dst = gin + row * W;
-        float left = 0.f, right = 0.f;
-        for (int xx = lane; xx < Wp; xx += 32) {
-            float cs = 0.f;
-            for (int yy = 0; yy <= yhi - ylo; ++yy) cs += __ldg(src + (long)yy * Wp + xx);
-            const int x = xx - pad;
-            if (x <= 0)
-                left += cs;            // padded columns 0 .. pad feed output column 0
-            else if (x >= W - 1)
-                right += cs;           // padded columns W-1+pad .. Wp-1 feed output column W-1
-            else
-                dst[x] = cs;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            left += __shfl_xor_sync(0xffffffffu, left, o);
-            right += __shfl_xor_sync(0xffffffffu, right, o);
-        }
-        if (lane == 0) {
-            if (W == 1) {
-                dst[0] = left + right;
-            } else {
-                dst[0] = left;
-                dst[W - 1] = right;
-            }
-        }
+    __shared__ float s_red[16];
+    const int nb = (H >= 2) ? 2 : 1;               // border rows per image
+    const long border_ctas = (long)N * nb;
+    if (blockIdx.x < border_ctas) {
+        const long img = blockIdx.x / nb;
+        const int y = (blockIdx.x % nb == 0) ? 0 : H - 1;
+        reppad_bwd_row<256>(gpad, gin, img * H + y, H, W, pad, threadIdx.x, s_red);
+        return;
     }
+    const int ni = H - nb;                         // interior rows per image
+    const long r = (long)(blockIdx.x - border_ctas) * 8 + (threadIdx.x >> 5);
+    if (ni <= 0 || r >= (long)N * ni) return;
+    const long img = r / ni;
+    const int y = 1 + (int)(r % ni);
+    reppad_bwd_row<32>(gpad, gin, img * H + y, H, W, pad, threadIdx.x & 31, nullptr);
+}
+
+static inline unsigned reppad_bwd_grid(int N, int H)
+{
+    const int nb = (H >= 2) ? 2 : 1;
+    const long interior = (long)N * (H - nb);
+    return (unsigned)((long)N * nb + (interior + 7) / 8);
 }
 
 // gD1 = a*gP + g1, gD2 = b*gP + g2 (null inputs are zero)
@@ -620,7 +662,7 @@ extern "C" int tai_fused_backward_b200(const float *grad_pred, const float *grad
             if (rc == TAI_OK) {
                 {
                     TimingScope ts("reppad_bwd", st, 0.0, 4.0 * ((double)B * C * (H + ks - 1) * (W + ks - 1) + n));
-                    reppad_bwd_kernel<<<ew_grid((long)B * C * H * 32, 256), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
+                    reppad_bwd_kernel<<<reppad_bwd_grid(B * C, H), 256, 0, st>>>(gpad, gdst, B * C, H, W, ks / 2);
                 }
                 rc = check_launch("reppad_bwd_kernel");
             }
@@ -646,6 +688,6 @@ extern "C" int replication_pad_backward_b200(const float *grad_out, float *grad_
     const long n = (long)N * H * W;
     TAI_REQUIRE(fits_int31((long)N * (H + 2 * p) * (W + 2 * p)), TAI_ERR_TOO_LARGE,
                 "replication_pad_backward_b200: tensor has >= 2^31 elements");
-    reppad_bwd_kernel<<<ew_grid((long)N * H * 32, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, N, H, W, p);
+    reppad_bwd_kernel<<<reppad_bwd_grid(N, H), 256, 0, (cudaStream_t)stream>>>(grad_out, grad_in, N, H, W, p);
     return check_launch("reppad_bwd_kernel");
 }
