@@ -170,6 +170,17 @@ int upsample_bilinear2x_backward_b200(const float *grad_out, float *grad_in, lon
 int unpool_add_forward_b200(const float *x, const float *res, float *out, long long N, int H, int W, void *stream);
 int unpool_backward_b200(const float *grad_out, float *grad_x, long long N, int H, int W, void *stream);
 
+/* 2 x 2 max pooling, stride 2, floor mode:
+ * replaces nn.MaxPool2d(2) of src/models/mcnet/mcnet.py:28-45 (motion / content encoders) and
+ * src/models/slomo/slomo.py:47-85.  in [N,H,W] -> out [N,H/2,W/2] and code [N,H/2,W/2] (one byte per output:
+ * 2*dy+dx of the selected element; scan order (0,0),(0,1),(1,0),(1,1), a later element wins only if greater
+ * or NaN -- the library's rule, so ties behind a ReLU go to the first position).  Backward writes EVERY element
+ * of grad_in [N,H,W] once (zeros for non-selected positions and for the unpooled last row / column of odd
+ * sizes): the caller's buffer needs no zero-fill.  H, W >= 2. */
+int maxpool2x2_forward_b200(const float *in, float *out, unsigned char *code, long long N, int H, int W, void *stream);
+int maxpool2x2_backward_b200(const float *grad_out, const unsigned char *code, float *grad_in, long long N, int H, int W,
+                             void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Reconstruction losses of the training step: MSELoss + GDL of a prediction
  * against the ground truth in one pass, with the inverse transform v01 = (v + add) * mul folded in.

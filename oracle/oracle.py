@@ -406,6 +406,34 @@ def fixed_unpooling(x):
     return out
 
 
+def maxpool2x2(x):
+    """nn.MaxPool2d(2) (mcnet.py:28-45; slomo.py:47-85): floor mode.  Returns (values, code) with code =
+    2*dy+dx of the selected element under the library kernel's rule: scan (0,0),(0,1),(1,0),(1,1), a later
+    element replaces the current one only if it is greater or NaN (first maximum wins ties)."""
+    x = np.asarray(x)
+    H, W = x.shape[-2:]
+    Ho, Wo = H // 2, W // 2
+    win = [x[..., dy:2 * Ho:2, dx:2 * Wo:2] for dy in (0, 1) for dx in (0, 1)]
+    m = win[0].copy()
+    code = np.zeros(m.shape, np.uint8)
+    for k in (1, 2, 3):
+        take = (win[k] > m) | np.isnan(win[k])
+        m = np.where(take, win[k], m)
+        code = np.where(take, np.uint8(k), code)
+    return m, code
+
+
+def maxpool2x2_backward(gout, code, H, W):
+    """Gradient routed to the selected element; zeros elsewhere (and in the unpooled last row / column)."""
+    gout = np.asarray(gout)
+    g = np.zeros(gout.shape[:-2] + (H, W), gout.dtype)
+    Ho, Wo = H // 2, W // 2
+    for k in range(4):
+        dy, dx = k // 2, k % 2
+        g[..., dy:2 * Ho:2, dx:2 * Wo:2] = np.where(code == k, gout, 0)
+    return g
+
+
 def upsample_bilinear2x_taps(n_in):
     """Integer taps and FP32 weights of the torch-0.3.1 bilinear x2 upsample along one axis (the library
     computed src = d * ((in-1)/(out-1)) in FP32, i0 = (int)src, i1 = i0 + (i0 < in-1), lambda = src - i0).

@@ -12,7 +12,8 @@ on torch's CPU kernels), with every hot-path operator replaced by the reference'
 * ConvLSTM gates          -> the chunk / sigmoid / tanh / cat chain of mcnet.py:287-293;
 * FlowWarper               -> host meshgrid + F.grid_sample with the torch-0.3.1 mapping (slomo.py:265-286);
 * DecCnn unpool + add      -> the permute / cat / clone().zero_() chain of mcnet.py:240-256 and the add of 234-236;
-* nn.Upsample (bilinear)   -> F.interpolate(align_corners=True), the torch-0.3.1 mapping.
+* nn.Upsample (bilinear)   -> F.interpolate(align_corners=True), the torch-0.3.1 mapping;
+* nn.MaxPool2d(2)          -> F.max_pool2d (the library op the reference calls).
 
 Used by bench.py (``cpu_baseline`` and ``--impl reference``) and by tests as an end-to-end checker of
 the GPU model.  Never imported by the product package.
@@ -24,7 +25,7 @@ import torch.nn.functional as F
 from oracle import oracle as O
 from video_frame_inpainting_b200.discriminators.SNDiscriminator import SNDiscriminator
 from video_frame_inpainting_b200.losses.losses import GDL
-from video_frame_inpainting_b200.models.layers import BilinearUp2
+from video_frame_inpainting_b200.models.layers import BilinearUp2, MaxPool2
 from video_frame_inpainting_b200.models.mcnet.mcnet import ConvLstmCell, DecCnn
 from video_frame_inpainting_b200.models.slomo.slomo import FlowWarper, SloMo
 from video_frame_inpainting_b200.models.tai.tai import TAI
@@ -100,6 +101,13 @@ class CpuFlowWarper(FlowWarper):
         return F.grid_sample(img, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
 
 
+class CpuMaxPool2(MaxPool2):
+    """nn.MaxPool2d(2) as the reference calls it (mcnet.py:28-45; slomo.py:47-85)."""
+
+    def forward(self, x):
+        return F.max_pool2d(x, 2)
+
+
 class CpuSloMo(SloMo):
     """Always the composed formulation of slomo.py:311-340 (no fused kernels)."""
 
@@ -123,6 +131,8 @@ def to_cpu_reference(model):
             m.__class__ = CpuDecCnn
         elif type(m) is BilinearUp2:
             m.__class__ = CpuBilinearUp2
+        elif type(m) is MaxPool2:
+            m.__class__ = CpuMaxPool2
         elif isinstance(m, TAI) and not isinstance(m, CpuTAIMixin):
             m.__class__ = type('Cpu' + type(m).__name__, (CpuTAIMixin, type(m)), {})
             m.separableConvolution = CpuSeparableConvolution.apply

@@ -200,3 +200,26 @@ def test_loss_oracle_matches_reference_gdl_golden():
     b = (torch.from_numpy(z["y0"]) + 1.) / 2
     assert abs(GDL()(a, b).item() - float(z["gdl0"])) < 1e-6
     assert GDL(reduce=False)(a, b).shape == a.shape[:-2] + (a.shape[-2] - 1, a.shape[-1] - 1)
+
+
+def test_maxpool_oracle_matches_library_op_including_ties():
+    """Tie rule of nn.MaxPool2d (first maximum in scan order, NaN wins): the oracle's codes must reproduce the
+    indices torch's CPU kernel returns, on ReLU-like inputs full of equal zeros and on odd sizes."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    for shape in [(2, 3, 8, 12), (1, 2, 7, 9), (1, 1, 2, 2)]:
+        x = np.maximum(rng.normal(size=shape), 0).astype(np.float32)     # ~half of the elements are exactly 0
+        x[0, 0, 0, 1] = np.nan
+        m, code = O.maxpool2x2(x)
+        ref, idx = F.max_pool2d(torch.from_numpy(x), 2, return_indices=True)
+        assert np.array_equal(m, ref.numpy(), equal_nan=True)
+        H, W = shape[-2:]
+        yy, xx = np.meshgrid(np.arange(H // 2), np.arange(W // 2), indexing="ij")
+        flat = (2 * yy + code // 2) * W + 2 * xx + code % 2
+        assert np.array_equal(flat, idx.numpy())
+        g = rng.normal(size=m.shape).astype(np.float32)
+        t = torch.from_numpy(np.nan_to_num(x)).requires_grad_()
+        F.max_pool2d(t, 2).backward(torch.from_numpy(g))
+        _, code2 = O.maxpool2x2(np.nan_to_num(x))
+        assert np.array_equal(O.maxpool2x2_backward(g, code2, H, W), t.grad.numpy())

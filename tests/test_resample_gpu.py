@@ -80,3 +80,33 @@ def test_unpool_add_forward_backward(cuda, B, C, H, W):
     b = tr.clone().requires_grad_()
     ops.UnpoolAddFunction.apply(a, b).backward(tg)
     assert torch.equal(b.grad, tg) and np.array_equal(a.grad.cpu().numpy(), gx)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 8, 12), (1, 2, 7, 9), (1, 1, 2, 2), (4, 64, 128, 128), (2, 5, 6, 10), (1, 3, 33, 64)])
+def test_maxpool2x2_forward_backward(cuda, B, C, H, W):
+    """Values, the 2-bit position codes (bit-exact, ties and NaN included) and the routed gradient; also against
+    the library op the reference called (indices of F.max_pool2d on the same device)."""
+    import torch
+    import torch.nn.functional as F
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(33)
+    x = np.maximum(rng.normal(size=(B, C, H, W)), 0).astype(np.float32)   # ReLU output: many exact ties at 0
+    x[0, 0, 1, 0] = np.nan
+    g = rng.normal(size=(B, C, H // 2, W // 2)).astype(np.float32)
+    tx, tg = to_cuda(x, g)
+    out, code = ops.maxpool2x2_forward(tx)
+    m, c = O.maxpool2x2(x)
+    assert np.array_equal(out.cpu().numpy(), m, equal_nan=True)
+    assert np.array_equal(code.cpu().numpy(), c)
+    gin = ops.maxpool2x2_backward(tg, code, H, W).cpu().numpy()
+    assert np.array_equal(gin, O.maxpool2x2_backward(g, c, H, W))
+    ref, idx = F.max_pool2d(tx, 2, return_indices=True)
+    yy, xx = torch.meshgrid(torch.arange(H // 2, device=cuda), torch.arange(W // 2, device=cuda), indexing="ij")
+    flat = (2 * yy + (code // 2).long()) * W + 2 * xx + (code % 2).long()
+    assert torch.equal(flat.expand_as(idx), idx)
+    # autograd route
+    a = torch.from_numpy(np.nan_to_num(x)).cuda().requires_grad_()
+    ops.MaxPool2x2Function.apply(a).backward(tg)
+    b = torch.from_numpy(np.nan_to_num(x)).cuda().requires_grad_()
+    F.max_pool2d(b, 2).backward(tg)
+    assert torch.equal(a.grad, b.grad)

@@ -40,6 +40,8 @@ SIGNATURES = {
     "upsample_bilinear2x_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "unpool_add_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "unpool_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
+    "maxpool2x2_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
+    "maxpool2x2_backward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "l2_gdl_loss_workspace_bytes": (ctypes.c_longlong, [ctypes.c_longlong] + [_c_i] * 2),
     "l2_gdl_loss_forward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [ctypes.c_float] * 2 + [_c_f] * 2 + [_c_s]),
     "l2_gdl_loss_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [ctypes.c_float] * 2 + [_c_f] * 3 + [_c_s]),

@@ -357,6 +357,95 @@ unpool_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, long N
     }
 }
 
+// ---- 2 x 2 max pooling (nn.MaxPool2d(2): mcnet.py:28-45, slomo.py:47-85) ------------------------------
+// out[n,y,x] = max of in[n, 2y..2y+1, 2x..2x+1]; the position of the maximum is kept as a 2-bit code (one byte
+// per output element) instead of the library's int64 flat index: the backward kernel reads 1 B instead of 8 B
+// per output element and writes every input-gradient element exactly once (no zero-fill + scatter).
+// Selection rule of the library kernel (max_pool_forward_nchw): scan (0,0), (0,1), (1,0), (1,1), take a later
+// element only if it is GREATER or NaN -- so ties (the zeros behind a ReLU) go to the first position.  The
+// code is the integer part of the op and is compared bit-exactly in the tests.  Odd H / W: floor mode, the
+// last row / column is not pooled and receives a zero gradient.
+__device__ __forceinline__ void mp_pick(float v, int k, float &m, int &code)
+{
+    if (v > m || v != v) {
+        m = v;
+        code = k;
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+maxpool2x2_fwd_kernel(const float *__restrict__ in, float *__restrict__ out, unsigned char *__restrict__ code, long N, int H,
+                      int W)
+{
+    const int Ho = H / 2, Wo = W / 2;
+    const int wq = VEC ? Wo / 2 : Wo;  // VEC: two outputs (four input columns) per thread
+    const long total = N * Ho * wq;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(idx % wq);
+        const long row = idx / wq;  // n * Ho + y
+        const int y = (int)(row % Ho);
+        const long n = row / Ho;
+        const float *p = in + (n * H + 2 * y) * W;
+        if (VEC) {
+            const float4 a = ld_stream4(reinterpret_cast<const float4 *>(p + 4 * q));
+            const float4 b = ld_stream4(reinterpret_cast<const float4 *>(p + W + 4 * q));
+            float m0 = a.x, m1 = a.z;
+            int c0 = 0, c1 = 0;
+            mp_pick(a.y, 1, m0, c0); mp_pick(b.x, 2, m0, c0); mp_pick(b.y, 3, m0, c0);
+            mp_pick(a.w, 1, m1, c1); mp_pick(b.z, 2, m1, c1); mp_pick(b.w, 3, m1, c1);
+            *reinterpret_cast<float2 *>(out + row * Wo + 2 * q) = make_float2(m0, m1);
+            *reinterpret_cast<uchar2 *>(code + row * Wo + 2 * q) = make_uchar2((unsigned char)c0, (unsigned char)c1);
+        } else {
+            float m = p[2 * q];
+            int c = 0;
+            mp_pick(p[2 * q + 1], 1, m, c); mp_pick(p[W + 2 * q], 2, m, c); mp_pick(p[W + 2 * q + 1], 3, m, c);
+            out[row * Wo + q] = m;
+            code[row * Wo + q] = (unsigned char)c;
+        }
+    }
+}
+
+// gin[n, 2y+dy, 2x+dx] = (code[n,y,x] == 2*dy+dx) ? gout[n,y,x] : 0; unpooled last row / column: 0
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+maxpool2x2_bwd_kernel(const float *__restrict__ gout, const unsigned char *__restrict__ code, float *__restrict__ gin, long N,
+                      int H, int W)
+{
+    const int Ho = H / 2, Wo = W / 2;
+    if (VEC) {  // H, W even here: every input element belongs to a window
+        const int wq = Wo / 2;
+        const long total = N * Ho * wq;
+        for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+            const int q = (int)(idx % wq);
+            const long row = idx / wq;
+            const int y = (int)(row % Ho);
+            const long n = row / Ho;
+            const float2 g = *reinterpret_cast<const float2 *>(gout + row * Wo + 2 * q);
+            const uchar2 c = *reinterpret_cast<const uchar2 *>(code + row * Wo + 2 * q);
+            float *p = gin + (n * H + 2 * y) * W + 4 * q;
+            *reinterpret_cast<float4 *>(p) = make_float4(c.x == 0 ? g.x : 0.f, c.x == 1 ? g.x : 0.f, c.y == 0 ? g.y : 0.f,
+                                                         c.y == 1 ? g.y : 0.f);
+            *reinterpret_cast<float4 *>(p + W) = make_float4(c.x == 2 ? g.x : 0.f, c.x == 3 ? g.x : 0.f, c.y == 2 ? g.y : 0.f,
+                                                             c.y == 3 ? g.y : 0.f);
+        }
+    } else {    // one thread per INPUT element
+        const long total = N * H * W;
+        for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+            const int x = (int)(idx % W);
+            const long row = idx / W;
+            const int y = (int)(row % H);
+            const long n = row / H;
+            float v = 0.f;
+            if ((y >> 1) < Ho && (x >> 1) < Wo) {
+                const long o = (n * Ho + (y >> 1)) * Wo + (x >> 1);
+                if (code[o] == (unsigned char)(2 * (y & 1) + (x & 1))) v = gout[o];
+            }
+            gin[idx] = v;
+        }
+    }
+}
+
 static int resample_args_ok(const char *who, const void *a, const void *b, long long N, int H, int W)
 {
     TAI_REQUIRE(a && b && N > 0 && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT, "%s: bad arguments N=%lld H=%d W=%d", who, N, H, W);
@@ -447,4 +536,35 @@ extern "C" int unpool_backward_b200(const float *grad_out, float *grad_x, long l
     else
         unpool_bwd_kernel<1><<<resample_grid(in_el, 256), 256, 0, st>>>(grad_out, grad_x, (long)N, H, W);
     return check_launch("unpool_bwd_kernel");
+}
+
+extern "C" int maxpool2x2_forward_b200(const float *in, float *out, unsigned char *code, long long N, int H, int W, void *stream)
+{
+    int rc = resample_args_ok("maxpool2x2_forward_b200", in, out, N, H, W);
+    if (rc != TAI_OK) return rc;
+    TAI_REQUIRE(code != nullptr && H >= 2 && W >= 2, TAI_ERR_INVALID_ARGUMENT, "maxpool2x2_forward_b200: needs H, W >= 2 and a code buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long out_el = (long)N * (H / 2) * (W / 2);
+    TimingScope ts("maxpool2x2_fwd", st, 0.0, 4.0 * N * H * W + 5.0 * out_el);  // read the input, write values + codes
+    if ((W % 4) == 0 && (H % 2) == 0 && aligned16(in, in) && (((uintptr_t)out & 7) == 0) && (((uintptr_t)code & 1) == 0))
+        maxpool2x2_fwd_kernel<true><<<resample_grid(out_el / 2, 256), 256, 0, st>>>(in, out, code, (long)N, H, W);
+    else
+        maxpool2x2_fwd_kernel<false><<<resample_grid(out_el, 256), 256, 0, st>>>(in, out, code, (long)N, H, W);
+    return check_launch("maxpool2x2_fwd_kernel");
+}
+
+extern "C" int maxpool2x2_backward_b200(const float *grad_out, const unsigned char *code, float *grad_in, long long N, int H, int W,
+                                        void *stream)
+{
+    int rc = resample_args_ok("maxpool2x2_backward_b200", grad_out, grad_in, N, H, W);
+    if (rc != TAI_OK) return rc;
+    TAI_REQUIRE(code != nullptr && H >= 2 && W >= 2, TAI_ERR_INVALID_ARGUMENT, "maxpool2x2_backward_b200: needs H, W >= 2 and a code buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long out_el = (long)N * (H / 2) * (W / 2);
+    TimingScope ts("maxpool2x2_bwd", st, 0.0, 4.0 * N * H * W + 5.0 * out_el);  // read gradients + codes, write the input gradient
+    if ((W % 4) == 0 && (H % 2) == 0 && aligned16(grad_in, grad_in) && (((uintptr_t)grad_out & 7) == 0) && (((uintptr_t)code & 1) == 0))
+        maxpool2x2_bwd_kernel<true><<<resample_grid(out_el / 2, 256), 256, 0, st>>>(grad_out, code, grad_in, (long)N, H, W);
+    else
+        maxpool2x2_bwd_kernel<false><<<resample_grid((long)N * H * W, 256), 256, 0, st>>>(grad_out, code, grad_in, (long)N, H, W);
+    return check_launch("maxpool2x2_bwd_kernel");
 }

@@ -14,6 +14,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from ... import ops
+from ..layers import MaxPool2
 from ...util.util import bgr2gray, bgr2gray_batched, inverse_transform
 
 
@@ -34,9 +35,9 @@ class MotionEnc(nn.Module):
     def __init__(self, gf_dim):
         super(MotionEnc, self).__init__()
         self.dyn_conv1 = nn.Sequential(nn.Conv2d(1, gf_dim, 5, padding=2), nn.ReLU())
-        self.dyn_conv2 = nn.Sequential(nn.MaxPool2d(2), nn.Conv2d(gf_dim, gf_dim * 2, 5, padding=2), nn.ReLU())
-        self.dyn_conv3 = nn.Sequential(nn.MaxPool2d(2), nn.Conv2d(gf_dim * 2, gf_dim * 4, 7, padding=3), nn.ReLU())
-        self.pool3 = nn.MaxPool2d(2)
+        self.dyn_conv2 = nn.Sequential(MaxPool2(), nn.Conv2d(gf_dim, gf_dim * 2, 5, padding=2), nn.ReLU())
+        self.dyn_conv3 = nn.Sequential(MaxPool2(), nn.Conv2d(gf_dim * 2, gf_dim * 4, 7, padding=3), nn.ReLU())
+        self.pool3 = MaxPool2()
 
     def forward(self, input_diff):
         skips = []
@@ -53,10 +54,10 @@ class ContentEnc(nn.Module):
     def __init__(self, c_dim, gf_dim):
         super(ContentEnc, self).__init__()
         self.cont_conv1 = nn.Sequential(*_conv_relu_chain([c_dim, gf_dim, gf_dim], 3))
-        self.cont_conv2 = nn.Sequential(nn.MaxPool2d(2), *_conv_relu_chain([gf_dim, gf_dim * 2, gf_dim * 2], 3))
-        self.cont_conv3 = nn.Sequential(nn.MaxPool2d(2),
+        self.cont_conv2 = nn.Sequential(MaxPool2(), *_conv_relu_chain([gf_dim, gf_dim * 2, gf_dim * 2], 3))
+        self.cont_conv3 = nn.Sequential(MaxPool2(),
                                         *_conv_relu_chain([gf_dim * 2, gf_dim * 4, gf_dim * 4, gf_dim * 4], 3))
-        self.pool3 = nn.MaxPool2d(2)
+        self.pool3 = MaxPool2()
 
     def forward(self, raw):
         skips = []

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ..layers import BilinearUp2
+from ..layers import BilinearUp2, MaxPool2
 
 
 def _up2():
@@ -28,7 +28,7 @@ def _up2():
 
 
 def _stage(cin, cmid, cout, k, alpha, pool):
-    layers = [nn.MaxPool2d(2)] if pool else []
+    layers = [MaxPool2()] if pool else []
     layers += [nn.Conv2d(cin, cmid, k, padding=k // 2), nn.LeakyReLU(alpha),
                nn.Conv2d(cmid, cout, k, padding=k // 2), nn.LeakyReLU(alpha)]
     return nn.Sequential(*layers)

@@ -305,6 +305,46 @@ class UnpoolAddFunction(torch.autograd.Function):
         return gx, (grad_out if ctx.needs[1] else None)
 
 
+def maxpool2x2_forward(x):
+    """nn.MaxPool2d(2) (mcnet.py:28-45; slomo.py:47-85): returns (out, code) -- code is the 2-bit position of
+    the selected element, one byte per output element (the library keeps an int64 flat index)."""
+    dev = _check("maxpool2x2_forward", x)
+    H, W = x.shape[-2:]
+    assert H >= 2 and W >= 2
+    planes = x.numel() // (H * W)
+    with torch.cuda.device(dev):
+        out = torch.empty(x.shape[:-2] + (H // 2, W // 2), device=dev, dtype=torch.float32)
+        code = torch.empty(out.shape, device=dev, dtype=torch.uint8)
+        _lib.call("maxpool2x2_forward_b200", _ptr(x), _ptr(out), _ptr(code), planes, H, W, _stream())
+    return out, code
+
+
+def maxpool2x2_backward(grad_out, code, H, W):
+    dev = _check("maxpool2x2_backward", grad_out)
+    assert code.is_cuda and code.dtype == torch.uint8 and code.is_contiguous() and code.shape == grad_out.shape
+    planes = grad_out.numel() // (grad_out.shape[-2] * grad_out.shape[-1])
+    with torch.cuda.device(dev):
+        gin = torch.empty(grad_out.shape[:-2] + (H, W), device=dev, dtype=torch.float32)
+        _lib.call("maxpool2x2_backward_b200", _ptr(grad_out), _ptr(code), _ptr(gin), planes, H, W, _stream())
+    return gin
+
+
+class MaxPool2x2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        out, code = maxpool2x2_forward(x)
+        ctx.save_for_backward(code)
+        ctx.hw = x.shape[-2:]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (code,) = ctx.saved_tensors
+        return maxpool2x2_backward(grad_out.contiguous(), code, *ctx.hw)
+
+
 # ------------------------------------------------------------------------------------------------
 # Super SloMo warp / blend
 # ------------------------------------------------------------------------------------------------
