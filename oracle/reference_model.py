@@ -121,6 +121,8 @@ class CpuSloMo(SloMo):
 def to_cpu_reference(model):
     """Re-class the hot-path modules of a (CPU-resident) product model to their reference formulations."""
     for m in model.modules():
+        if hasattr(m, 'batch_streams'):
+            m.batch_streams = False      # the reference runs the two MC-Net streams back to back (tai.py:77-84)
         if type(m) is ConvLstmCell:
             m.__class__ = CpuConvLstmCell
         elif type(m) is FlowWarper:
