@@ -208,6 +208,10 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0, graph=Tr
     model = create_model(key)
     if os.environ.get("TAI_BATCH_STREAMS") in ("0", "1") and hasattr(model, "batch_streams"):
         model.batch_streams = os.environ["TAI_BATCH_STREAMS"] == "1"   # A/B switch for profiles/; default: model's own
+    if os.environ.get("TAI_BATCH_HISTORY") in ("0", "1"):
+        for m in model.modules():
+            if hasattr(m, "batch_history"):
+                m.batch_history = os.environ["TAI_BATCH_HISTORY"] == "1"
     if os.environ.get("TAI_BATCH_TIME") in ("0", "1") and hasattr(model, "batch_time"):
         model.batch_time = os.environ["TAI_BATCH_TIME"] == "1"
     if training:

@@ -124,6 +124,8 @@ def to_cpu_reference(model):
         if hasattr(m, 'batch_streams'):
             m.batch_streams = False      # the reference runs the two MC-Net streams back to back (tai.py:77-84)
             m.batch_time = False         # ... and the kernel network once per middle frame (tai.py:91-105)
+        if hasattr(m, 'batch_history'):
+            m.batch_history = False      # one motion-encoder call per known difference frame (mcnet.py:405-409)
         if type(m) is ConvLstmCell:
             m.__class__ = CpuConvLstmCell
         elif type(m) is FlowWarper:

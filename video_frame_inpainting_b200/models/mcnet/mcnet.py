@@ -168,6 +168,8 @@ class MCNet(nn.Module):
         self.residual1 = Residual(gf_dim * 2, gf_dim * 1)
         self.dec_cnn = DecCnn(c_dim, gf_dim)
 
+    batch_history = True  # see forward(); the CPU port of the reference switches it off
+
     def get_initial_conv_lstm_state(self, batch_size, image_size):
         ref = next(self.parameters())
         return torch.zeros(batch_size, 8 * self.gf_dim, image_size[0] // 8, image_size[1] // 8,
@@ -182,10 +184,20 @@ class MCNet(nn.Module):
         image_size = xt.shape[2:4]
         state = self.get_initial_conv_lstm_state(xt.shape[0], image_size)
 
-        # motion history
-        for t in range(K - 1):
-            enc_h, res_m = self.motion_enc(diffs[t])
+        # motion history (mcnet.py:405-409 encodes the K-1 known difference frames one by one; the encoder has no
+        # state, so all but the last go through it as ONE batch -- the last stays separate because its skip
+        # activations res_m are the ones the decoder uses -- and only the ConvLSTM walks them in order)
+        if self.batch_history and K - 1 >= 3:
+            N = xt.shape[0]
+            enc_all, _ = self.motion_enc(torch.cat(diffs[:K - 2], 0))
+            for enc_h in enc_all.view(K - 2, N, *enc_all.shape[1:]).unbind(0):
+                h_dyn, state = self.conv_lstm_cell(enc_h, state)
+            enc_h, res_m = self.motion_enc(diffs[K - 2])
             h_dyn, state = self.conv_lstm_cell(enc_h, state)
+        else:
+            for t in range(K - 1):
+                enc_h, res_m = self.motion_enc(diffs[t])
+                h_dyn, state = self.conv_lstm_cell(enc_h, state)
 
         pred, dyn, cont, res = [], [], [], []
         for t in range(T):
