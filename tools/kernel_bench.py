@@ -44,7 +44,7 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # 256 MB > 126 MB L2
     cases = {
-        "kth": (32, 1, 128, 128, 51), "kth1": (1, 1, 128, 128, 51), "ucf": (8, 3, 240, 320, 51),
+        "kth": (32, 1, 128, 128, 51), "kth1": (1, 1, 128, 128, 51), "kth160": (160, 1, 128, 128, 51), "ucf": (8, 3, 240, 320, 51),
         "small": (16, 1, 128, 128, 13), "mid": (16, 3, 256, 256, 25),
     }
     g = torch.Generator(device=dev).manual_seed(0)

@@ -13,10 +13,19 @@ x = torch.randn(B, C, H, W, device=dev)
 g = torch.randn(B, C, 2 * H, 2 * W, device=dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 conv, state = torch.randn(32, 1024, 16, 16, device=dev), torch.randn(32, 512, 16, 16, device=dev)
+gns = torch.randn_like(state)
+a, b = torch.rand(160, 1, 128, 128, device=dev) * 2 - 1, torch.rand(160, 1, 128, 128, device=dev) * 2 - 1
+one = torch.ones(1, device=dev)
 for _ in range(3):
     flush.zero_()
     ops.upsample_bilinear2x_backward(g)
     ops.upsample_bilinear2x_forward(x)
     ops.convlstm_gates_forward(conv, state, 1.0)
+    ops.convlstm_gates_backward(conv, state, gns, 1.0)
     ops.unpool_backward(g)
+    ops.unpool_add_forward(x, g)
+    out, code = ops.maxpool2x2_forward(g)
+    ops.maxpool2x2_backward(out, code, 2 * H, 2 * W)
+    ops.l2_gdl_loss_forward(a, b)
+    ops.l2_gdl_loss_backward(a, b, one, one)
 torch.cuda.synchronize()
