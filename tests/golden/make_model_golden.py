@@ -1,0 +1,135 @@
+"""Generates tests/golden/tai_model_ref.npz by IMPORTING the reference's own model classes
+(/root/reference/src/models/{tai,mcnet}/*.py, unmodified) and running them on CPU tensors.
+
+Run in the build container only (the reference is not present on the GPU box):
+
+    python tests/golden/make_model_golden.py
+
+The reference is Python-2 / torch-0.3.1 code with no CPU implementation of its operator, so the import needs
+shims.  Each one is listed here because it bounds what the fixture pins:
+
+  * ``xrange`` -> ``range``; a ``Queue`` module (util.py:5); stub modules for matplotlib / tensorboardX / imageio /
+    skimage (plotting and logging, never executed here); a stub ``_ext.cunnex`` (the cffi extension).
+  * ``src.separable_convolution.SeparableConvolution.SeparableConvolution`` is replaced by the C port of the
+    reference kernels (oracle/reference_model.py: CpuSeparableConvolution, pinned separately against the reference's
+    CUDA kernels) -- the reference operator raises NotImplementedError on CPU tensors (SeparableConvolution.py:48-49).
+  * ``Tensor.cuda`` is the identity (tai.py:72,216 and mcnet.py:386 move helper tensors to the GPU unconditionally).
+  * Python-2 integer division: ``nn.Conv2d`` paddings and ``torch.zeros`` sizes are coerced to int
+    (mcnet.py:278 ``(feature_size - 1) / 2``, mcnet.py:384 ``image_size[0]/8``).
+  * ``nn.Upsample(mode='bilinear')`` is evaluated with ``align_corners=True``: torch 0.3.1's only bilinear mapping.
+    (This one is an assumption about the un-vendored library, see oracle/oracle.py's header: the fixture pins the
+    model's composition, not that mapping.)
+
+What the fixture therefore pins, through the reference's own code: the module tree and every state_dict key and
+shape (checkpoint compatibility), the order of the forward / backward streams and the time reversal, the residual
+merging, the time-ratio injection, the ConvLSTM gate chain, the zero-insertion unpooling chain, the gray /
+difference-frame prologue and the 0.5 / 0.5 blend.
+"""
+import builtins
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def install_shims():
+    import queue
+    builtins.xrange = range
+    q = types.ModuleType('Queue')
+    q.Queue = queue.Queue
+    sys.modules['Queue'] = q
+    mpl = types.ModuleType('matplotlib')
+    mpl.use = lambda *a, **k: None
+    sys.modules['matplotlib'] = mpl
+    sys.modules['matplotlib.pyplot'] = types.ModuleType('matplotlib.pyplot')
+    for name in ('tensorboardX', 'imageio', 'skimage', 'skimage.measure'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    ext = types.ModuleType('_ext')
+    ext.cunnex = types.ModuleType('_ext.cunnex')
+    sys.modules['_ext'] = ext
+    sys.modules['_ext.cunnex'] = ext.cunnex
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+    conv_init = nn.Conv2d.__init__
+
+    def conv_init_int(self, *args, **kwargs):
+        if 'padding' in kwargs and isinstance(kwargs['padding'], float):
+            kwargs['padding'] = int(kwargs['padding'])
+        conv_init(self, *args, **kwargs)
+    nn.Conv2d.__init__ = conv_init_int
+
+    zeros = torch.zeros
+
+    def zeros_int(*size, **kwargs):
+        return zeros(*[int(s) if isinstance(s, float) else s for s in size], **kwargs)
+    torch.zeros = zeros_int
+
+    def upsample_forward(self, x):
+        assert self.mode == 'bilinear'
+        return F.interpolate(x, scale_factor=self.scale_factor, mode='bilinear', align_corners=True)
+    nn.Upsample.forward = upsample_forward
+
+
+def main():
+    install_shims()
+    sys.path.insert(0, '/root/reference')
+    from oracle.reference_model import CpuSeparableConvolution
+    import src.separable_convolution.SeparableConvolution as ref_op
+    ref_op.SeparableConvolution = CpuSeparableConvolution
+    import src.models.tai.tai as ref_tai
+    import src.util.util as ref_util
+
+    out = {}
+    cases = [dict(gf_dim=4, c_dim=1, feature_size=3, ks=13, num_block=5, kf_dim=4, K=3, T=2, F_=3, H=32, W=32, B=2),
+             dict(gf_dim=4, c_dim=3, feature_size=3, ks=5, num_block=4, kf_dim=2, K=2, T=3, F_=3, H=32, W=48, B=1)]
+    for ci, c in enumerate(cases):
+        torch.manual_seed(100 + ci)
+        model = ref_tai.TAIFillInModel(c['gf_dim'], c['c_dim'], c['feature_size'], c['ks'], num_block=c['num_block'],
+                                       kf_dim=c['kf_dim'])
+        model.apply(ref_util.weights_init)
+        # xavier weights make this small network's outputs vanish; scale the biases up so that every branch carries signal
+        g = torch.Generator().manual_seed(200 + ci)
+        for name, p in model.named_parameters():
+            if name.endswith('bias'):
+                p.data.uniform_(-0.1, 0.1, generator=g)
+        pre = torch.rand(c['B'], c['K'], c['c_dim'], c['H'], c['W'], generator=g) * 2 - 1
+        fol = torch.rand(c['B'], c['F_'], c['c_dim'], c['H'], c['W'], generator=g) * 2 - 1
+        res = model(c['T'], pre, fol)
+        loss = res['pred'].pow(2).mean() + res['pred_forward'].mean() + res['pred_backward'].pow(2).mean()
+        loss.backward()
+        tag = 'c%d_' % ci
+        for k, v in c.items():
+            out[tag + 'cfg_' + k] = np.int64(v)
+        out[tag + 'pre'] = pre.numpy()
+        out[tag + 'fol'] = fol.numpy()
+        for k, v in res.items():
+            out[tag + 'out_' + k] = v.detach().numpy()
+        names = []
+        for name, v in model.state_dict().items():
+            names.append(name)
+            out[tag + 'sd_' + name] = v.numpy()
+        out[tag + 'sd_names'] = np.array(names)
+        # gradients of a few parameters spread over the network (first / last layers of each sub-network)
+        picks = [n for n, _ in model.named_parameters()]
+        picks = [picks[0], picks[len(picks) // 3], picks[2 * len(picks) // 3], picks[-1]]
+        params = dict(model.named_parameters())
+        for n in picks:
+            out[tag + 'grad_' + n] = params[n].grad.numpy()
+        out[tag + 'grad_names'] = np.array(picks)
+        print('case', ci, 'params', sum(p.numel() for p in model.parameters()), 'pred rms', float(res['pred'].pow(2).mean().sqrt()))
+    out['n'] = np.int64(len(cases))
+    path = os.path.join(HERE, 'tai_model_ref.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KB')
+
+
+if __name__ == '__main__':
+    main()

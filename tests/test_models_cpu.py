@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import oracle as O
 from oracle.reference_model import CpuTAITrainingStep, to_cpu_reference
 from video_frame_inpainting_b200.losses.losses import GDL
 from video_frame_inpainting_b200.models.create_model import create_model
@@ -101,3 +102,37 @@ def test_cpu_reference_training_step_decreases_nothing_weird():
     changed = sum(int(not torch.equal(a, b)) for a, b in zip(before, st.generator.parameters()))
     # merge_residual1 is computed but never consumed by the kernel net (tai.py:47,93 vs 221-226): no gradient
     assert changed >= len(before) - 4
+
+
+def _golden_case(z, ci):
+    tag = 'c%d_' % ci
+    cfg = {k[len(tag) + 4:]: int(z[k]) for k in z.files if k.startswith(tag + 'cfg_')}
+    sd = {str(n): torch.from_numpy(z[tag + 'sd_' + str(n)]) for n in z[tag + 'sd_names']}
+    model = TAIFillInModel(cfg['gf_dim'], cfg['c_dim'], cfg['feature_size'], cfg['ks'], num_block=cfg['num_block'],
+                           kf_dim=cfg['kf_dim'])
+    return tag, cfg, sd, model
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_reference_model_classes_golden(ci):
+    """tests/golden/tai_model_ref.npz holds a state_dict, inputs, outputs and gradients produced by the REFERENCE's
+    own TAIFillInModel / MCNet / TAI classes (imported unmodified by tests/golden/make_model_golden.py, whose
+    header lists the shims).  (1) checkpoint compatibility: the reference state_dict loads with strict=True --
+    every key and shape matches; (2) the CPU port used as the end-to-end checker (oracle/reference_model.py)
+    reproduces the reference's outputs and gradients."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    tag, cfg, sd, model = _golden_case(z, ci)
+    assert list(model.state_dict().keys()) == list(sd.keys())          # same names in the same order
+    model.load_state_dict(sd, strict=True)
+    model = to_cpu_reference(model)
+    pre, fol = torch.from_numpy(z[tag + 'pre']), torch.from_numpy(z[tag + 'fol'])
+    out = model(cfg['T'], pre, fol)
+    for k in ('pred', 'pred_forward', 'pred_backward', 'interp_net_outputs_1', 'interp_net_outputs_2'):
+        ref = z[tag + 'out_' + k]
+        assert out[k].shape == ref.shape
+        assert O.rel_err(out[k].detach().numpy(), ref) < 1e-5, k
+    (out['pred'].pow(2).mean() + out['pred_forward'].mean() + out['pred_backward'].pow(2).mean()).backward()
+    params = dict(model.named_parameters())
+    for n in z[tag + 'grad_names']:
+        assert O.rel_err(params[str(n)].grad.numpy(), z[tag + 'grad_' + str(n)]) < 1e-4, n

@@ -177,3 +177,27 @@ def test_batched_streams_equal_separate_streams(cuda, kind):
     model.batch_streams = model.batch_time = True
     out = model(2, pre, fol[:, :2])                              # K = 4, F = 2: separate passes
     assert out['pred'].shape == (2, 2, 1, 32, 32)
+
+
+@pytest.mark.parametrize("ci", [0, 1])
+def test_gpu_model_matches_reference_classes_golden(cuda, ci):
+    """The product model on the GPU (cuDNN convolutions + this library's kernels, batched loop structure) with
+    a state_dict produced by the REFERENCE's own classes, against the outputs and gradients those classes
+    produced (tests/golden/tai_model_ref.npz, generated by tests/golden/make_model_golden.py)."""
+    import os
+    _strict_fp32()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    tag = 'c%d_' % ci
+    cfg = {k[len(tag) + 4:]: int(z[k]) for k in z.files if k.startswith(tag + 'cfg_')}
+    sd = {str(n): torch.from_numpy(z[tag + 'sd_' + str(n)]) for n in z[tag + 'sd_names']}
+    model = TAIFillInModel(cfg['gf_dim'], cfg['c_dim'], cfg['feature_size'], cfg['ks'], num_block=cfg['num_block'],
+                           kf_dim=cfg['kf_dim'])
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    out = model(cfg['T'], torch.from_numpy(z[tag + 'pre']).cuda(), torch.from_numpy(z[tag + 'fol']).cuda())
+    for k in ('pred', 'pred_forward', 'pred_backward', 'interp_net_outputs_1', 'interp_net_outputs_2'):
+        assert O.rel_err(out[k].detach().cpu().numpy(), z[tag + 'out_' + k]) < 2e-3, k
+    (out['pred'].pow(2).mean() + out['pred_forward'].mean() + out['pred_backward'].pow(2).mean()).backward()
+    params = dict(model.named_parameters())
+    for n in z[tag + 'grad_names']:
+        assert O.rel_err(params[str(n)].grad.cpu().numpy(), z[tag + 'grad_' + str(n)]) < 2e-2, n
