@@ -16,9 +16,9 @@ shims.  Each one is listed here because it bounds what the fixture pins:
   * ``Tensor.cuda`` is the identity (tai.py:72,216 and mcnet.py:386 move helper tensors to the GPU unconditionally).
   * Python-2 integer division: ``nn.Conv2d`` paddings and ``torch.zeros`` sizes are coerced to int
     (mcnet.py:278 ``(feature_size - 1) / 2``, mcnet.py:384 ``image_size[0]/8``).
-  * ``nn.Upsample(mode='bilinear')`` is evaluated with ``align_corners=True``: torch 0.3.1's only bilinear mapping.
-    (This one is an assumption about the un-vendored library, see oracle/oracle.py's header: the fixture pins the
-    model's composition, not that mapping.)
+  * ``nn.Upsample(mode='bilinear')`` and ``F.grid_sample`` are evaluated with ``align_corners=True``: torch 0.3.1's
+    only mapping.  (This one is an assumption about the un-vendored library, see oracle/oracle.py's header: the
+    fixture pins the models' composition, not that mapping.)
 
 What the fixture therefore pins, through the reference's own code: the module tree and every state_dict key and
 shape (checkpoint compatibility), the order of the forward / backward streams and the time reversal, the residual
@@ -77,6 +77,12 @@ def install_shims():
         return F.interpolate(x, scale_factor=self.scale_factor, mode='bilinear', align_corners=True)
     nn.Upsample.forward = upsample_forward
 
+    grid_sample = F.grid_sample
+
+    def grid_sample_031(img, grid, *a, **k):   # torch 0.3.1: bilinear, zero padding, ix = ((g + 1) / 2) * (W - 1)
+        return grid_sample(img, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
+    F.grid_sample = grid_sample_031
+
 
 def main():
     install_shims()
@@ -125,6 +131,35 @@ def main():
             out[tag + 'grad_' + n] = params[n].grad.numpy()
         out[tag + 'grad_names'] = np.array(picks)
         print('case', ci, 'params', sum(p.numel() for p in model.parameters()), 'pred rms', float(res['pred'].pow(2).mean().sqrt()))
+    # Super SloMo baseline (src/models/slomo/slomo.py): flow combination, warps, refinement, visibility blend, and
+    # the reversed time order in which the reference concatenates its predictions (slomo.py:331-340)
+    import src.models.slomo.slomo as ref_slomo
+    torch.manual_seed(300)
+    sm = ref_slomo.SloMoFillInModel(gf_dim=2, c_input_dim=3)
+    sm.apply(ref_util.weights_init)
+    g = torch.Generator().manual_seed(301)
+    for name, p in sm.named_parameters():
+        if name.endswith('bias'):
+            p.data.uniform_(-0.1, 0.1, generator=g)
+        else:
+            p.data.mul_(3.0)              # flows of a few pixels instead of ~0
+    pre = torch.rand(1, 2, 3, 32, 64, generator=g) * 2 - 1
+    fol = torch.rand(1, 2, 3, 32, 64, generator=g) * 2 - 1
+    res = sm(3, pre, fol)
+    res['pred'].pow(2).mean().backward()
+    out['s_pre'], out['s_fol'] = pre.numpy(), fol.numpy()
+    for k, v in res.items():
+        out['s_out_' + k] = v.detach().numpy()
+    names = []
+    for name, v in sm.state_dict().items():
+        names.append(name)
+        out['s_sd_' + name] = v.numpy()
+    out['s_sd_names'] = np.array(names)
+    first = [n for n, _ in sm.named_parameters()][0]
+    out['s_grad_name'] = np.array([first])
+    out['s_grad'] = dict(sm.named_parameters())[first].grad.numpy()
+    print('slomo params', sum(p.numel() for p in sm.parameters()), 'pred rms', float(res['pred'].detach().pow(2).mean().sqrt()),
+          'flow rms', float(res['F_0_1'].detach().pow(2).mean().sqrt()))
     out['n'] = np.int64(len(cases))
     path = os.path.join(HERE, 'tai_model_ref.npz')
     np.savez_compressed(path, **out)

@@ -136,3 +136,22 @@ def test_reference_model_classes_golden(ci):
     params = dict(model.named_parameters())
     for n in z[tag + 'grad_names']:
         assert O.rel_err(params[str(n)].grad.numpy(), z[tag + 'grad_' + str(n)]) < 1e-4, n
+
+
+def test_reference_slomo_classes_golden():
+    """Same pin for the Super SloMo baseline (the reference's own slomo.py classes): strict state_dict load, the
+    five outputs (incl. the reversed time order of the collectors, slomo.py:331-340) and a gradient."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    sd = {str(n): torch.from_numpy(z['s_sd_' + str(n)]) for n in z['s_sd_names']}
+    model = SloMoFillInModel(gf_dim=2, c_input_dim=3)
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    model = to_cpu_reference(model)
+    out = model(3, torch.from_numpy(z['s_pre']), torch.from_numpy(z['s_fol']))
+    for k in ('pred', 'F_0_1', 'F_1_0', 'F_t_0_collector', 'F_t_1_collector'):
+        assert out[k].shape == z['s_out_' + k].shape
+        assert O.rel_err(out[k].detach().numpy(), z['s_out_' + k]) < 1e-5, k
+    out['pred'].pow(2).mean().backward()
+    name = str(z['s_grad_name'][0])
+    assert O.rel_err(dict(model.named_parameters())[name].grad.numpy(), z['s_grad']) < 1e-4

@@ -201,3 +201,25 @@ def test_gpu_model_matches_reference_classes_golden(cuda, ci):
     params = dict(model.named_parameters())
     for n in z[tag + 'grad_names']:
         assert O.rel_err(params[str(n)].grad.cpu().numpy(), z[tag + 'grad_' + str(n)]) < 2e-2, n
+
+
+def test_gpu_slomo_matches_reference_classes_golden(cuda):
+    """Super SloMo on the GPU (fused flow-combine / warp / refine / blend kernels in eval mode, FlowWarper kernel
+    with autograd in train mode) against outputs of the reference's own slomo.py classes."""
+    import os
+    _strict_fp32()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    sd = {str(n): torch.from_numpy(z['s_sd_' + str(n)]) for n in z['s_sd_names']}
+    model = SloMoFillInModel(gf_dim=2, c_input_dim=3)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    pre, fol = torch.from_numpy(z['s_pre']).cuda(), torch.from_numpy(z['s_fol']).cuda()
+    with torch.no_grad():
+        out = model.eval()(3, pre, fol)
+    for k in ('pred', 'F_0_1', 'F_1_0', 'F_t_0_collector', 'F_t_1_collector'):
+        assert O.rel_err(out[k].cpu().numpy(), z['s_out_' + k]) < 2e-3, k
+    out_t = model.train()(3, pre, fol)
+    assert O.rel_err(out_t['pred'].detach().cpu().numpy(), z['s_out_pred']) < 2e-3
+    out_t['pred'].pow(2).mean().backward()
+    name = str(z['s_grad_name'][0])
+    assert O.rel_err(dict(model.named_parameters())[name].grad.cpu().numpy(), z['s_grad']) < 2e-2
