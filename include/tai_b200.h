@@ -201,6 +201,15 @@ int l2_gdl_loss_backward_b200(const float *pred, const float *target, long long 
                               const float *grad_mse, const float *grad_gdl, float *grad_pred, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Output side: frames in [-1, 1] -> 8-bit interleaved images.
+ * replaces, per frame, predict.py:124-134 (save_video_frames: torch.clamp(video, -1, 1), to_numpy,
+ * (255 * inverse_transform(frame)).astype(np.uint8), [:, :, ::-1] for colour) before the PNG encoder.
+ * frames [N,C,H,W] float -> out [N,H,W,C] bytes; flip_channels != 0 reverses the channel order (BGR -> RGB).
+ * Same FP32 operation order as the reference, truncation toward zero: byte-exact. */
+int frames_to_uint8_b200(const float *frames, unsigned char *out, long long N, int C, int H, int W, int flip_channels,
+                         void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helper: a pure FFMA loop, used by bench.py to report the on-box FP32 FMA
  * ceiling next to the nominal 148 x 128 x 2 x f_SM.  Writes one float per thread to `sink`
  * (gridDim*blockDim floats).  flops = 2 * 8 * iters * grid * block. */

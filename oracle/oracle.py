@@ -527,6 +527,15 @@ def l2_gdl_loss_backward(pred, target, g_mse, g_gdl, add=1.0, mul=0.5):
     return g.reshape(shape)
 
 
+def frames_to_uint8(video):
+    """predict.py:124-134 (save_video_frames) up to the PNG encoder: [T,C,H,W] float in [-1,1] ->
+    [T,H,W,C] uint8, FP32 arithmetic as numpy evaluates the reference expression, RGB order for C == 3."""
+    v = np.clip(np.asarray(video, np.float32), np.float32(-1), np.float32(1))
+    frames = np.transpose(v, (0, 2, 3, 1))                          # to_numpy(..., transpose=(1, 2, 0)) per frame
+    u8 = (255 * ((frames + 1.) / 2)).astype(np.uint8)               # util.py:22-23 inside predict.py:132
+    return u8[..., ::-1] if video.shape[1] == 3 else u8
+
+
 def rel_err(x, ref):
     """max |x-ref| / max(|ref|, rms(ref)) -- the tolerance definition of SURVEY.md section 7
     (V/H are unnormalised and signed, so outputs have zero crossings)."""

@@ -119,3 +119,34 @@ def test_slomo_fused_stages(cuda, B, C, H, W, T):
         out = ops.slomo_refine_blend(t_i0, t_i1, ft0, ft1, t_d0, t_d1, t_v0, t).cpu().numpy()
         ref = O.slomo_refine_blend(i0, i1, ft0.cpu().numpy(), ft1.cpu().numpy(), d0, d1, v0, t)
         assert_close(out, ref, tol=2e-3, what="refine+blend")
+
+
+def test_frames_to_uint8_and_png_layout(cuda, tmp_path):
+    """Device-side float -> 8-bit conversion, byte-exact against PNGs written by the reference's own
+    save_video_frames (tests/golden/frames_u8_ref.npz), and the predict.py file layout."""
+    import os
+    import torch
+    from PIL import Image
+    from video_frame_inpainting_b200 import ops, predict
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "frames_u8_ref.npz"))
+    for C in (1, 3):
+        video = torch.from_numpy(z['video_c%d' % C]).cuda()
+        u8 = ops.frames_to_uint8(video).cpu().numpy()
+        png = z['png_c%d' % C]
+        assert np.array_equal(u8[..., 0] if C == 1 else u8, png)
+        assert np.array_equal(u8, O.frames_to_uint8(z['video_c%d' % C]))
+    B, K, T, F_, C, H, W = 2, 2, 3, 2, 3, 16, 24
+    g = torch.Generator().manual_seed(3)
+    pre, mid, fol = (torch.rand(B, n, C, H + 4, W, generator=g) * 2 - 1 for n in (K, T, F_))
+    out = {'pred': mid.cuda() * 0.9, 'pred_forward': mid.cuda() * 0.5}
+    files = predict.write_clip_predictions(out, pre, fol, ['vidA_0', 'vidB_7'], str(tmp_path), (H, W),
+                                           gt_middle_frames=mid, intermediate_preds=True)
+    names = sorted(os.listdir(os.path.join(str(tmp_path), 'vidB_7')))
+    assert names == sorted(['gt_preceding_%04d.png' % t for t in range(K)] + ['gt_middle_%04d.png' % (K + t) for t in range(T)]
+                           + ['gt_following_%04d.png' % (K + T + t) for t in range(F_)]
+                           + ['pred_middle_%04d.png' % (K + t) for t in range(T)]
+                           + ['pred_middle_forward_%04d.png' % (K + t) for t in range(T)])
+    assert len(files) == 2 * len(names)
+    img = np.array(Image.open(os.path.join(str(tmp_path), 'vidA_0', 'pred_middle_%04d.png' % K)))
+    assert img.shape == (H, W, 3)
+    assert np.array_equal(img, O.frames_to_uint8((mid[0, :1, :, :H, :W] * 0.9).numpy())[0])

@@ -223,3 +223,14 @@ def test_maxpool_oracle_matches_library_op_including_ties():
         F.max_pool2d(t, 2).backward(torch.from_numpy(g))
         _, code2 = O.maxpool2x2(np.nan_to_num(x))
         assert np.array_equal(O.maxpool2x2_backward(g, code2, H, W), t.grad.numpy())
+
+
+def test_frames_to_uint8_oracle_matches_reference_save_video_frames():
+    """tests/golden/frames_u8_ref.npz: PNGs written by the reference's own save_video_frames (predict.py:113-134,
+    executed verbatim by tests/golden/make_frames_golden.py), incl. values on / next to every 8-bit bin edge."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "frames_u8_ref.npz"))
+    for C in (1, 3):
+        u8 = O.frames_to_uint8(z['video_c%d' % C])
+        png = z['png_c%d' % C]
+        assert np.array_equal(u8[..., 0] if C == 1 else u8, png)

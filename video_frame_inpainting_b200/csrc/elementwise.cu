@@ -367,6 +367,27 @@ slomo_refine_blend_kernel(const float *__restrict__ i0, const float *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Output side of predict.py: frames in [-1, 1] -> 8-bit images (predict.py:124-134: clamp(-1, 1),
+// (255 * ((x + 1.) / 2)).astype(uint8), BGR -> RGB for colour).  in [N,C,H,W] float -> out [N,H,W,C] bytes, the
+// layout PIL / PNG encoders take; the device-to-host copy shrinks 4x.  FP32 arithmetic in the reference's order
+// (the +1, the /2 and the *255 each round once; truncation toward zero): byte-exact.
+__global__ void __launch_bounds__(256)
+frames_to_u8_kernel(const float *__restrict__ in, unsigned char *__restrict__ out, long N, int C, long hw, int flip)
+{
+    const long n = N * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / hw;
+        const long pix = idx - b * hw;
+        for (int c = 0; c < C; ++c) {
+            const float x = ld_stream(in + (b * C + (flip ? C - 1 - c : c)) * hw + pix);
+            const float v = fminf(fmaxf(x, -1.f), 1.f);
+            const float s = __fmul_rn(255.f, __fmul_rn(__fadd_rn(v, 1.f), 0.5f));
+            out[idx * C + c] = (unsigned char)(int)s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FFMA probe: 8 independent chains per thread, `iters` FMAs each (scalar FFMA or packed FFMA2).
 template <bool PACKED>
 __global__ void ffma_probe_kernel(float *sink, int iters)
@@ -515,6 +536,17 @@ extern "C" int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
     slomo_refine_blend_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
         i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, (float)(1.0 - t), (float)t, out, B, C, H, W);
     return check_launch("slomo_refine_blend_kernel");
+}
+
+extern "C" int frames_to_uint8_b200(const float *frames, unsigned char *out, long long N, int C, int H, int W, int flip_channels,
+                                    void *stream)
+{
+    TAI_REQUIRE(frames && out && N > 0 && C > 0 && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT, "frames_to_uint8_b200: bad arguments");
+    TAI_REQUIRE(fits_int31(N * (long long)C * H * W), TAI_ERR_TOO_LARGE, "frames_to_uint8_b200: tensor has >= 2^31 elements");
+    cudaStream_t st = (cudaStream_t)stream;
+    TimingScope ts("frames_to_u8", st, 0.0, 5.0 * N * C * H * W);
+    frames_to_u8_kernel<<<stream_grid((long)N * H * W, 256), 256, 0, st>>>(frames, out, (long)N, C, (long)H * W, flip_channels ? 1 : 0);
+    return check_launch("frames_to_u8_kernel");
 }
 
 extern "C" int tai_b200_ffma_probe(float *sink, int grid, int block, int iters, int packed, void *stream)

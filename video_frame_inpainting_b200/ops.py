@@ -469,6 +469,19 @@ def l2_gdl_loss(pred, target, add=1.0, mul=0.5):
     return L2GDLLossFunction.apply(pred, target, add, mul)
 
 
+def frames_to_uint8(frames, flip_channels=None):
+    """[..., C, H, W] float in [-1, 1] -> [..., H, W, C] uint8 as predict.py:124-134 forms it (clamp, inverse
+    transform, *255, truncation; BGR -> RGB when C == 3 unless flip_channels says otherwise)."""
+    dev = _check("frames_to_uint8", frames)
+    C, H, W = frames.shape[-3:]
+    N = frames.numel() // (C * H * W)
+    flip = (C == 3) if flip_channels is None else bool(flip_channels)
+    with torch.cuda.device(dev):
+        out = torch.empty(frames.shape[:-3] + (H, W, C), device=dev, dtype=torch.uint8)
+        _lib.call("frames_to_uint8_b200", _ptr(frames), _ptr(out), N, C, H, W, int(flip), _stream())
+    return out
+
+
 def ffma_probe(grid, block, iters, packed=False):
     """Launch the pure-FFMA probe kernel; returns the sink tensor (flops = 2*8*iters*grid*block)."""
     sink = torch.empty(grid * block, device="cuda", dtype=torch.float32)
