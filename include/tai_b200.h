@@ -201,6 +201,21 @@ int l2_gdl_loss_backward_b200(const float *pred, const float *target, long long 
                               const float *grad_mse, const float *grad_gdl, float *grad_pred, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Bias + activation epilogue of the convolution layers and its adjoint (one pass each way).
+ * replaces, around every `nn.Conv2d(bias=True)` [+ nn.ReLU / nn.LeakyReLU] of src/models/mcnet/mcnet.py:28-45,79-104,
+ * 137-225, src/models/tai/tai.py:244-347 and src/models/slomo/slomo.py:28-260, the library's broadcast add_(bias),
+ * clamp_min / leaky_relu, threshold_backward / leaky_relu_backward and the sum over (N,H,W) for the bias gradient.
+ * act: 0 none, 1 relu, 2 leaky relu (negative slope alpha).
+ * forward, IN PLACE on the convolution output y [N,C,HW]:  y = act(y + bias[c])  (same two FP32 ops as the library).
+ * backward: grad_in = grad_out * act'(out) (act' from the forward OUTPUT, as the library does; grad_in may be NULL for
+ * act == 0, where it would equal grad_out) and grad_bias[c] = sum over n, hw of grad_in (fixed-order two-stage sum in
+ * `workspace` of bias_act_backward_workspace_bytes(N, C) bytes: deterministic). */
+int bias_act_forward_b200(float *y, const float *bias, long long N, int C, int HW, int act, float alpha, void *stream);
+long long bias_act_backward_workspace_bytes(long long N, int C);
+int bias_act_backward_b200(const float *grad_out, const float *out, float *grad_in, float *grad_bias, void *workspace,
+                           long long N, int C, int HW, int act, float alpha, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Output side: frames in [-1, 1] -> 8-bit interleaved images.
  * replaces, per frame, predict.py:124-134 (save_video_frames: torch.clamp(video, -1, 1), to_numpy,
  * (255 * inverse_transform(frame)).astype(np.uint8), [:, :, ::-1] for colour) before the PNG encoder.

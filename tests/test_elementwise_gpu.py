@@ -150,3 +150,59 @@ def test_frames_to_uint8_and_png_layout(cuda, tmp_path):
     img = np.array(Image.open(os.path.join(str(tmp_path), 'vidA_0', 'pred_middle_%04d.png' % K)))
     assert img.shape == (H, W, 3)
     assert np.array_equal(img, O.frames_to_uint8((mid[0, :1, :, :H, :W] * 0.9).numpy())[0])
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 5, 6, 8), (3, 7, 5, 3), (64, 64, 32, 32), (1, 1, 1, 1), (4, 130, 4, 4)])
+@pytest.mark.parametrize("act,alpha", [("relu", 0.0), ("leaky", 0.1), ("none", 0.0)])
+def test_bias_act_matches_library_ops(cuda, N, C, H, W, act, alpha):
+    """Bias + activation epilogue against the library ops it replaces (broadcast add, relu / leaky_relu, their
+    backward and the bias-gradient sum): forward bit-identical, input gradient bit-identical, bias gradient to
+    1e-5 (another summation order)."""
+    import torch
+    import torch.nn.functional as F
+    from video_frame_inpainting_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(50)
+    y = torch.randn(N, C, H, W, device=cuda, generator=g)
+    b = torch.randn(C, device=cuda, generator=g)
+    go = torch.randn(N, C, H, W, device=cuda, generator=g)
+    y_ref = y.clone().requires_grad_()
+    b_ref = b.clone().requires_grad_()
+    pre = y_ref + b_ref.view(1, C, 1, 1)
+    ref = {"relu": F.relu, "leaky": lambda t: F.leaky_relu(t, alpha), "none": lambda t: t}[act](pre)
+    ref.backward(go)
+    y2 = (y.clone().requires_grad_() * 1.0)          # a non-leaf the Function may overwrite in place
+    b2 = b.clone().requires_grad_()
+    src = y2
+    out = ops.BiasActFunction.apply(y2, b2, act, alpha)
+    assert out.data_ptr() == src.data_ptr()           # in place
+    assert torch.equal(out, ref)
+    gin, gb = ops.bias_act_backward(go, out.detach(), act, alpha)
+    assert torch.equal(gin, y_ref.grad)
+    assert_close(gb.cpu().numpy(), b_ref.grad.cpu().numpy(), tol=1e-5, what="bias gradient")
+    assert torch.equal(gb, ops.bias_act_backward(go, out.detach(), act, alpha)[1]), "deterministic"
+
+
+def test_fused_sequential_equals_plain_sequential(cuda):
+    """FusedSequential (bias-free convolution + bias/activation pass) against nn.Sequential with the same children:
+    same state_dict keys, same outputs, same gradients."""
+    import torch
+    import torch.nn as nn
+    from video_frame_inpainting_b200.models.layers import FusedSequential
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    mods = lambda: [nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 8, 5, padding=2), nn.LeakyReLU(0.1),
+                    nn.ConvTranspose2d(8, 4, 3, padding=1), nn.ReLU(), nn.Conv2d(4, 2, 1), nn.Tanh()]
+    plain = nn.Sequential(*mods()).cuda()
+    fused = FusedSequential(*mods()).cuda()
+    assert list(plain.state_dict().keys()) == list(fused.state_dict().keys())
+    fused.load_state_dict(plain.state_dict())
+    x = torch.randn(2, 3, 16, 20, device=cuda)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    ya, yb = plain(xa), fused(xb)
+    assert_close(yb.detach().cpu().numpy(), ya.detach().cpu().numpy(), tol=1e-5, what="fused sequential fwd")
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    assert_close(xb.grad.cpu().numpy(), xa.grad.cpu().numpy(), tol=1e-4, what="fused sequential grad x")
+    for (n, pa), (_, pb) in zip(plain.named_parameters(), fused.named_parameters()):
+        assert_close(pb.grad.cpu().numpy(), pa.grad.cpu().numpy(), tol=1e-4, what="fused sequential grad " + n)

@@ -1,6 +1,7 @@
 """Parameter-free layers shared by the model families; each one stands for a library module of the
 reference and routes it to a kernel of this library."""
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import ops
 
@@ -29,3 +30,36 @@ class MaxPool2(nn.Module):
 
     def extra_repr(self):
         return "kernel_size=2, stride=2"
+
+
+class FusedSequential(nn.Sequential):
+    """``nn.Sequential`` with the reference's children under the reference's names (state_dict keys unchanged) whose
+    forward evaluates every ``nn.Conv2d`` / ``nn.ConvTranspose2d`` with bias [+ ``nn.ReLU`` / ``nn.LeakyReLU``] as a bias-free cuDNN
+    convolution followed by ONE bias + activation pass of this library (``bias_act_forward_b200``, in place on
+    the convolution output), instead of the library's broadcast ``add_``, ``clamp_min`` and, backward,
+    ``threshold_backward`` and the bias-gradient ``sum``.  Same FP32 operations, same results.  CPU tensors take
+    the plain route (the CPU port of the reference model)."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if (type(m) in (nn.Conv2d, nn.ConvTranspose2d) and m.bias is not None and x.is_cuda and m.padding_mode == 'zeros'
+                    and x.dtype == m.weight.dtype):
+                act, alpha, used = "none", 0.0, 1
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if type(nxt) is nn.ReLU:
+                    act, used = "relu", 2
+                elif type(nxt) is nn.LeakyReLU:
+                    act, alpha, used = "leaky", nxt.negative_slope, 2
+                if type(m) is nn.Conv2d:
+                    y = F.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+                else:
+                    y = F.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+                x = ops.BiasActFunction.apply(y.contiguous(), m.bias, act, alpha)
+                i += used
+            else:
+                x = m(x)
+                i += 1
+        return x

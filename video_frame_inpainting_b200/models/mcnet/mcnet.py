@@ -14,7 +14,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from ... import ops
-from ..layers import MaxPool2
+from ..layers import FusedSequential, MaxPool2
 from ...util.util import bgr2gray, bgr2gray_batched, inverse_transform
 
 
@@ -34,9 +34,9 @@ class MotionEnc(nn.Module):
 
     def __init__(self, gf_dim):
         super(MotionEnc, self).__init__()
-        self.dyn_conv1 = nn.Sequential(nn.Conv2d(1, gf_dim, 5, padding=2), nn.ReLU())
-        self.dyn_conv2 = nn.Sequential(MaxPool2(), nn.Conv2d(gf_dim, gf_dim * 2, 5, padding=2), nn.ReLU())
-        self.dyn_conv3 = nn.Sequential(MaxPool2(), nn.Conv2d(gf_dim * 2, gf_dim * 4, 7, padding=3), nn.ReLU())
+        self.dyn_conv1 = FusedSequential(nn.Conv2d(1, gf_dim, 5, padding=2), nn.ReLU())
+        self.dyn_conv2 = FusedSequential(MaxPool2(), nn.Conv2d(gf_dim, gf_dim * 2, 5, padding=2), nn.ReLU())
+        self.dyn_conv3 = FusedSequential(MaxPool2(), nn.Conv2d(gf_dim * 2, gf_dim * 4, 7, padding=3), nn.ReLU())
         self.pool3 = MaxPool2()
 
     def forward(self, input_diff):
@@ -53,9 +53,9 @@ class ContentEnc(nn.Module):
 
     def __init__(self, c_dim, gf_dim):
         super(ContentEnc, self).__init__()
-        self.cont_conv1 = nn.Sequential(*_conv_relu_chain([c_dim, gf_dim, gf_dim], 3))
-        self.cont_conv2 = nn.Sequential(MaxPool2(), *_conv_relu_chain([gf_dim, gf_dim * 2, gf_dim * 2], 3))
-        self.cont_conv3 = nn.Sequential(MaxPool2(),
+        self.cont_conv1 = FusedSequential(*_conv_relu_chain([c_dim, gf_dim, gf_dim], 3))
+        self.cont_conv2 = FusedSequential(MaxPool2(), *_conv_relu_chain([gf_dim, gf_dim * 2, gf_dim * 2], 3))
+        self.cont_conv3 = FusedSequential(MaxPool2(),
                                         *_conv_relu_chain([gf_dim * 2, gf_dim * 4, gf_dim * 4, gf_dim * 4], 3))
         self.pool3 = MaxPool2()
 
@@ -73,7 +73,7 @@ class CombLayers(nn.Module):
 
     def __init__(self, gf_dim):
         super(CombLayers, self).__init__()
-        self.h_comb = nn.Sequential(*_conv_relu_chain([gf_dim * 8, gf_dim * 4, gf_dim * 2, gf_dim * 4], 3))
+        self.h_comb = FusedSequential(*_conv_relu_chain([gf_dim * 8, gf_dim * 4, gf_dim * 2, gf_dim * 4], 3))
 
     def forward(self, h_dyn, h_cont):
         return self.h_comb(torch.cat((h_dyn, h_cont), dim=1))
@@ -84,7 +84,7 @@ class Residual(nn.Module):
 
     def __init__(self, in_dim, out_dim):
         super(Residual, self).__init__()
-        self.res = nn.Sequential(nn.Conv2d(in_dim, out_dim, 3, padding=1), nn.ReLU(),
+        self.res = FusedSequential(nn.Conv2d(in_dim, out_dim, 3, padding=1), nn.ReLU(),
                                  nn.Conv2d(out_dim, out_dim, 3, padding=1))
 
     def forward(self, input_dyn, input_cont):
@@ -97,9 +97,9 @@ class DecCnn(nn.Module):
 
     def __init__(self, c_dim, gf_dim):
         super(DecCnn, self).__init__()
-        self.dec3 = nn.Sequential(*_conv_relu_chain([gf_dim * 4, gf_dim * 4, gf_dim * 4, gf_dim * 2], 3, transposed=True))
-        self.dec2 = nn.Sequential(*_conv_relu_chain([gf_dim * 2, gf_dim * 2, gf_dim], 3, transposed=True))
-        self.dec1 = nn.Sequential(*_conv_relu_chain([gf_dim, gf_dim, c_dim], 3, transposed=True, last=nn.Tanh()))
+        self.dec3 = FusedSequential(*_conv_relu_chain([gf_dim * 4, gf_dim * 4, gf_dim * 4, gf_dim * 2], 3, transposed=True))
+        self.dec2 = FusedSequential(*_conv_relu_chain([gf_dim * 2, gf_dim * 2, gf_dim], 3, transposed=True))
+        self.dec1 = FusedSequential(*_conv_relu_chain([gf_dim, gf_dim, c_dim], 3, transposed=True, last=nn.Tanh()))
 
     def forward(self, comb, res1, res2, res3):
         dec3_out = self.dec3(self.unpool_add(comb, res3))
@@ -145,7 +145,13 @@ class ConvLstmCell(nn.Module):
 
     def forward(self, input, state):
         h = state[:, self.num_features:]
-        conv_output = self.conv(torch.cat((input, h), dim=1))
+        x = torch.cat((input, h), dim=1)
+        if x.is_cuda and self.conv.bias is not None:
+            # bias-free cuDNN convolution + one vectorised in-place bias pass (layers.FusedSequential explains why)
+            conv_output = F.conv2d(x, self.conv.weight, None, self.conv.stride, self.conv.padding)
+            conv_output = ops.BiasActFunction.apply(conv_output.contiguous(), self.conv.bias, "none", 0.0)
+        else:
+            conv_output = self.conv(x)
         new_state = self.gates(conv_output, state)
         return new_state[:, self.num_features:], new_state
 

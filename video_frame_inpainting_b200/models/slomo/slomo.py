@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ..layers import BilinearUp2, MaxPool2
+from ..layers import BilinearUp2, FusedSequential, MaxPool2
 
 
 def _up2():
@@ -31,7 +31,7 @@ def _stage(cin, cmid, cout, k, alpha, pool):
     layers = [MaxPool2()] if pool else []
     layers += [nn.Conv2d(cin, cmid, k, padding=k // 2), nn.LeakyReLU(alpha),
                nn.Conv2d(cmid, cout, k, padding=k // 2), nn.LeakyReLU(alpha)]
-    return nn.Sequential(*layers)
+    return FusedSequential(*layers)
 
 
 class Encoder(nn.Module):

@@ -23,7 +23,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from ... import ops
-from ..layers import BilinearUp2
+from ..layers import BilinearUp2, FusedSequential
 from ...separable_convolution.SeparableConvolution import SeparableConvolution
 from ..mcnet.mcnet import MCNet, Residual, gray_difference_frames
 
@@ -226,7 +226,7 @@ def create_basic_conv_block(num_layers, num_in_channels, num_out_channels):
     for _ in range(num_layers):
         seq += [nn.Conv2d(cin, num_out_channels, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False)]
         cin = num_out_channels
-    return nn.Sequential(*seq)
+    return FusedSequential(*seq)
 
 
 def create_1d_kernel_generator_block(num_layers, kf_dim, ks):
@@ -237,7 +237,7 @@ def create_1d_kernel_generator_block(num_layers, kf_dim, ks):
         cout = ks if i == num_layers - 1 else kf_dim * 2
         seq += [nn.Conv2d(kf_dim * 2, cout, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=False)]
     seq += [_up2(), nn.Conv2d(ks, ks, kernel_size=3, stride=1, padding=1)]
-    return nn.Sequential(*seq)
+    return FusedSequential(*seq)
 
 
 def create_encoder_blocks(start_i, end_i, layers, if_dim, kf_dim):
@@ -261,7 +261,7 @@ def create_decoder_blocks(num_block, kf_dim, layers, rc_loc):
         c_in = c_out if i == 0 else kf_dim * 2 ** (num_block - i + 1)
         deconvs.append(create_basic_conv_block(layers, c_in, c_out))
         extra = 1 if i == rc_loc - 1 else 0
-        upsamples.append(nn.Sequential(_up2(),
+        upsamples.append(FusedSequential(_up2(),
                                        nn.Conv2d(c_out + extra, c_out, kernel_size=3, stride=1, padding=1),
                                        nn.ReLU(inplace=False)))
     return deconvs, upsamples

@@ -469,6 +469,61 @@ def l2_gdl_loss(pred, target, add=1.0, mul=0.5):
     return L2GDLLossFunction.apply(pred, target, add, mul)
 
 
+# ------------------------------------------------------------------------------------------------
+# bias + activation epilogue of the convolution layers
+# ------------------------------------------------------------------------------------------------
+
+ACT_CODES = {"none": 0, "relu": 1, "leaky": 2}
+
+
+def bias_act_forward_(y, bias, act="relu", alpha=0.0):
+    """In place: y[N,C,...] = act(y + bias[c])."""
+    dev = _check("bias_act_forward_", y, bias)
+    N, C = y.shape[0], y.shape[1]
+    assert bias.shape == (C,)
+    with torch.cuda.device(dev):
+        _lib.call("bias_act_forward_b200", _ptr(y), _ptr(bias), N, C, y.numel() // (N * C), ACT_CODES[act], float(alpha),
+                  _stream())
+    return y
+
+
+def bias_act_backward(grad_out, out, act="relu", alpha=0.0):
+    """-> (grad_in, grad_bias); grad_in is grad_out itself for act == 'none'."""
+    dev = _check("bias_act_backward", grad_out, out)
+    N, C = grad_out.shape[0], grad_out.shape[1]
+    code = ACT_CODES[act]
+    with torch.cuda.device(dev):
+        gb = torch.empty(C, device=dev, dtype=torch.float32)
+        ws = torch.empty(max(int(_lib.load().bias_act_backward_workspace_bytes(N, C)), 4) // 4, device=dev,
+                         dtype=torch.float32)
+        gin = torch.empty_like(grad_out) if code != 0 else None
+        _lib.call("bias_act_backward_b200", _ptr(grad_out), _ptr(out), _ptr(gin), _ptr(gb), _ptr(ws), N, C,
+                  grad_out.numel() // (N * C), code, float(alpha), _stream())
+    return (gin if gin is not None else grad_out), gb
+
+
+class BiasActFunction(torch.autograd.Function):
+    """(y, bias) -> act(y + bias) IN PLACE on y, which must be the fresh output of a bias-free convolution (nothing
+    else may hold it: the convolution's own backward needs its input and weight only)."""
+
+    @staticmethod
+    def forward(ctx, y, bias, act, alpha):
+        assert y.is_contiguous()
+        bias_act_forward_(y, bias.contiguous(), act, alpha)
+        ctx.mark_dirty(y)
+        ctx.act, ctx.alpha = act, alpha
+        if act != "none":
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        out = ctx.saved_tensors[0] if ctx.act != "none" else None
+        gin, gb = bias_act_backward(grad_out.contiguous(), out, ctx.act, ctx.alpha)
+        return gin, gb, None, None
+
+
 def frames_to_uint8(frames, flip_channels=None):
     """[..., C, H, W] float in [-1, 1] -> [..., H, W, C] uint8 as predict.py:124-134 forms it (clamp, inverse
     transform, *255, truncation; BGR -> RGB when C == 3 unless flip_channels says otherwise)."""

@@ -46,9 +46,20 @@ def broadcast_module(module, src=0):
 
 
 class FlatGradAllReducer(object):
+    ALIGN = 32  # floats: 128 B
+
     def __init__(self, module, n_buckets=4):
         self.params = [p for p in module.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        # every gradient view starts on a 128 B boundary: autograd accumulates into the views in place
+        # (`grad += new`, once per use of a shared weight -- ~800 adds per KTH step), and torch's vectorised
+        # elementwise kernel needs 16 B-aligned operands; unaligned views fell back to the scalar kernel
+        # (785 launches, 23 ms per step)
+        align = self.ALIGN
+
+        def padded(n):
+            return (n + align - 1) // align * align
+
+        total = sum(padded(p.numel()) for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
         # gradients become available roughly in reverse parameter order: bucket 0 = last parameters
@@ -57,7 +68,7 @@ class FlatGradAllReducer(object):
         self.buckets, cur, cur_n = [], [], 0
         for p in order:
             cur.append(p)
-            cur_n += p.numel()
+            cur_n += padded(p.numel())
             if cur_n >= target:
                 self.buckets.append(cur)
                 cur, cur_n = [], 0
@@ -68,7 +79,7 @@ class FlatGradAllReducer(object):
         for bi, bucket in enumerate(self.buckets):
             hi = offset
             for p in bucket:
-                offset -= p.numel()
+                offset -= padded(p.numel())
                 p.grad = self.flat[offset:offset + p.numel()].view_as(p)
                 self._bucket_of[p] = bi
             self._slices.append((offset, hi))
