@@ -215,6 +215,11 @@ long long bias_act_backward_workspace_bytes(long long N, int C);
 int bias_act_backward_b200(const float *grad_out, const float *out, float *grad_in, float *grad_bias, void *workspace,
                            long long N, int C, int HW, int act, float alpha, void *stream);
 
+/* out = v / (sqrt(sum v^2) + eps) for one vector of n floats (one launch):
+ * replaces `_l2normalize` of src/discriminators/SNDiscriminator.py:5-7 (pow, sum, pow, add, div -- five launches,
+ * called twice per power iteration of every spectral-norm layer: 1170 times per KTH training step). */
+int l2_normalize_b200(const float *v, float *out, int n, float eps, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Output side: frames in [-1, 1] -> 8-bit interleaved images.
  * replaces, per frame, predict.py:124-134 (save_video_frames: torch.clamp(video, -1, 1), to_numpy,

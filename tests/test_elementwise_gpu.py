@@ -206,3 +206,29 @@ def test_fused_sequential_equals_plain_sequential(cuda):
     assert_close(xb.grad.cpu().numpy(), xa.grad.cpu().numpy(), tol=1e-4, what="fused sequential grad x")
     for (n, pa), (_, pb) in zip(plain.named_parameters(), fused.named_parameters()):
         assert_close(pb.grad.cpu().numpy(), pa.grad.cpu().numpy(), tol=1e-4, what="fused sequential grad " + n)
+
+
+def test_l2_normalize_and_sn_discriminator_route(cuda):
+    """One-launch l2 normalisation of the spectral-norm power iteration against the five-op library chain, and the
+    discriminator (bias + LeakyReLU epilogue, fused normalisation) against the same module on the CPU."""
+    import copy
+    import torch
+    from video_frame_inpainting_b200 import ops
+    from video_frame_inpainting_b200.discriminators.SNDiscriminator import SNDiscriminator
+    for n in (1, 7, 64, 513, 8192):
+        v = torch.randn(1, n, device=cuda)
+        ref = v / (((v ** 2).sum()) ** 0.5 + 1e-12)
+        assert_close(ops.l2_normalize(v).cpu().numpy(), ref.cpu().numpy(), tol=1e-6, what="l2 normalize")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    d_cpu = SNDiscriminator((32, 32), 1, 3, 8, 3)
+    d_gpu = copy.deepcopy(d_cpu).cuda()
+    x = torch.randn(2, 6, 1, 32, 32)
+    for _ in range(2):                     # two calls: the in-place weight normalisation and u carry over
+        a = d_cpu(x)
+        b = d_gpu(x.cuda())
+    assert_close(b.detach().cpu().numpy(), a.detach().numpy(), tol=1e-3, what="SN discriminator logits")
+    a.sum().backward()
+    b.sum().backward()
+    for (n_, pa), (_, pb) in zip(d_cpu.named_parameters(), d_gpu.named_parameters()):
+        assert_close(pb.grad.cpu().numpy(), pa.grad.numpy(), tol=2e-3, what="SN discriminator grad " + n_)

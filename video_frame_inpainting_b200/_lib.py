@@ -48,6 +48,7 @@ SIGNATURES = {
     "bias_act_forward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 3 + [ctypes.c_float, _c_s]),
     "bias_act_backward_workspace_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _c_i]),
     "bias_act_backward_b200": (_c_i, [_c_f] * 5 + [ctypes.c_longlong] + [_c_i] * 3 + [ctypes.c_float, _c_s]),
+    "l2_normalize_b200": (_c_i, [_c_f] * 2 + [_c_i, ctypes.c_float, _c_s]),
     "frames_to_uint8_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 4 + [_c_s]),
     "tai_b200_ffma_probe": (_c_i, [_c_f] + [_c_i] * 4 + [_c_s]),
 }

@@ -75,7 +75,28 @@ bias_act_bwd_kernel(const float *gout, const float *__restrict__ out, float *gin
             const float4 *g4 = reinterpret_cast<const float4 *>(gout + base);
             const float4 *o4 = reinterpret_cast<const float4 *>(out + base);
             float4 *d4 = reinterpret_cast<float4 *>(gin + base);
-            for (int i = threadIdx.x; i < HW / 4; i += 256) {
+            const int q = HW / 4;
+            int i = threadIdx.x;
+            for (; i + 768 < q; i += 1024) {  // four independent 128-bit pairs per trip: eight loads in flight
+                float4 g[4], o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) g[u] = g4[i + 256 * u];
+                if (act != ACT_NONE) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) o[u] = o4[i + 256 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        g[u].x = act_grad(g[u].x, o[u].x, act, alpha);
+                        g[u].y = act_grad(g[u].y, o[u].y, act, alpha);
+                        g[u].z = act_grad(g[u].z, o[u].z, act, alpha);
+                        g[u].w = act_grad(g[u].w, o[u].w, act, alpha);
+                        if (write_gin) d4[i + 256 * u] = g[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += (g[u].x + g[u].y) + (g[u].z + g[u].w);
+            }
+            for (; i < q; i += 256) {
                 float4 g = g4[i];
                 if (act != ACT_NONE) {
                     const float4 o = o4[i];
@@ -122,11 +143,41 @@ bias_grad_finalize_kernel(const float *__restrict__ partial, float *__restrict__
 
 static inline int bias_chunks(int N, int C)
 {
-    // enough CTAs to fill the chip (~8 per SM), at most one per plane
+    // enough CTAs to fill the chip (~8 per SM), at most one per plane -- and a divisor of N where one is close, so
+    // that every CTA of a channel owns the same number of planes (19 chunks over 64 planes: 4 vs 3.4 on average)
     int chunks = (sm_count() * 8 + C - 1) / C;
     if (chunks > N) chunks = N;
     if (chunks < 1) chunks = 1;
+    for (int d = chunks; d >= (chunks + 1) / 2; --d)
+        if (N % d == 0) return d;
     return chunks;
+}
+
+// v / (sqrt(sum v^2) + eps) for one short vector: the `_l2normalize` of the spectral-norm power iteration
+// (SNDiscriminator.py:5-7: pow, sum, pow, add, div = five launches, 1170 times per KTH training step).  One CTA.
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const float *__restrict__ v, float *__restrict__ out, int n, float eps)
+{
+    __shared__ float s_red[8];
+    __shared__ float s_inv;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float x = v[i];
+        acc = fmaf(x, x, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        s_inv = sqrtf(t) + eps;
+    }
+    __syncthreads();
+    const float d = s_inv;
+    for (int i = threadIdx.x; i < n; i += 256) out[i] = v[i] / d;
 }
 
 }  // namespace tai
@@ -187,4 +238,11 @@ extern "C" int bias_act_backward_b200(const float *grad_out, const float *out, f
     if (rc != TAI_OK) return rc;
     bias_grad_finalize_kernel<<<(C + 31) / 32, 32, 0, st>>>(partial, grad_bias, C, chunks);
     return check_launch("bias_grad_finalize_kernel");
+}
+
+extern "C" int l2_normalize_b200(const float *v, float *out, int n, float eps, void *stream)
+{
+    TAI_REQUIRE(v && out && n > 0, TAI_ERR_INVALID_ARGUMENT, "l2_normalize_b200: bad arguments");
+    l2_normalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(v, out, n, eps);
+    return check_launch("l2_normalize_kernel");
 }

@@ -1,5 +1,6 @@
 """Spectral-normalised video discriminator of the TAI training step (reference:
-src/discriminators/SNDiscriminator.py).  Training-step plumbing only -- no custom kernels.
+src/discriminators/SNDiscriminator.py).  Training-step plumbing; the only kernel it reaches is the bias +
+LeakyReLU epilogue of its convolutions (models/layers.py:FusedSequential).
 
 Behaviour kept from the reference: every forward runs ``Ip`` power iterations, divides ``weight.data`` by
 the estimated top singular value IN PLACE (SNDiscriminator.py:63-68, 87-92) and keeps the vector ``u``
@@ -12,8 +13,13 @@ import torch
 import torch.nn as nn
 from torch.nn import functional as F
 
+from .. import ops
+from ..models.layers import FusedSequential
+
 
 def _l2normalize(v, eps=1e-12):
+    if v.is_cuda and v.dtype == torch.float32 and not (torch.is_grad_enabled() and v.requires_grad):
+        return ops.l2_normalize(v.contiguous(), eps)    # one launch instead of five
     return v / (((v ** 2).sum()) ** 0.5 + eps)
 
 
@@ -38,10 +44,15 @@ class SNConv2d(nn.Conv2d):
         self.Ip = Ip
         self.u = None
 
-    def forward(self, input):
+    def normalized_weight(self):
+        """One spectral-norm update (power iteration + in-place division of ``weight.data``); returns the weight."""
         sigma, self.u = max_singular_value(self.weight.view(self.weight.size(0), -1), self.u, Ip=self.Ip)
         self.weight.data = self.weight.data / sigma
-        return F.conv2d(input, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return self.weight
+
+    def forward(self, input):
+        return F.conv2d(input, self.normalized_weight(), self.bias, self.stride, self.padding, self.dilation,
+                        self.groups)
 
 
 class SNLinear(nn.Linear):
@@ -71,7 +82,7 @@ class SNDiscriminator(nn.Module):
             cin = df_dim * mult
             h = floor((h + 2 * 1 - 4) / 2 + 1)
             w = floor((w + 2 * 1 - 4) / 2 + 1)
-        self.conv_layers = nn.Sequential(*layers)
+        self.conv_layers = FusedSequential(*layers)   # same children / keys; bias + LeakyReLU as one pass on CUDA
         self.num_sn_linear_in_feats = int(h * w * df_dim * 8)
         self.linear_layer = SNLinear(self.num_sn_linear_in_feats, 1, Ip=1)
 

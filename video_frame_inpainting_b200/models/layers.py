@@ -45,7 +45,9 @@ class FusedSequential(nn.Sequential):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if (type(m) in (nn.Conv2d, nn.ConvTranspose2d) and m.bias is not None and x.is_cuda and m.padding_mode == 'zeros'
+            sn = getattr(m, 'normalized_weight', None)   # spectral-norm convolution: its weight update comes first
+            if ((type(m) in (nn.Conv2d, nn.ConvTranspose2d) or (sn is not None and isinstance(m, nn.Conv2d)))
+                    and m.bias is not None and x.is_cuda and m.padding_mode == 'zeros'
                     and x.dtype == m.weight.dtype):
                 act, alpha, used = "none", 0.0, 1
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
@@ -53,8 +55,9 @@ class FusedSequential(nn.Sequential):
                     act, used = "relu", 2
                 elif type(nxt) is nn.LeakyReLU:
                     act, alpha, used = "leaky", nxt.negative_slope, 2
-                if type(m) is nn.Conv2d:
-                    y = F.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+                if isinstance(m, nn.Conv2d):
+                    w = sn() if sn is not None else m.weight
+                    y = F.conv2d(x, w, None, m.stride, m.padding, m.dilation, m.groups)
                 else:
                     y = F.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
                 x = ops.BiasActFunction.apply(y.contiguous(), m.bias, act, alpha)

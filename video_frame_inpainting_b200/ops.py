@@ -524,6 +524,15 @@ class BiasActFunction(torch.autograd.Function):
         return gin, gb, None, None
 
 
+def l2_normalize(v, eps=1e-12):
+    """v / (||v||_2 + eps) in one launch (SNDiscriminator.py:5-7); no autograd (the power iteration runs without)."""
+    dev = _check("l2_normalize", v)
+    with torch.cuda.device(dev):
+        out = torch.empty_like(v)
+        _lib.call("l2_normalize_b200", _ptr(v), _ptr(out), v.numel(), float(eps), _stream())
+    return out
+
+
 def frames_to_uint8(frames, flip_channels=None):
     """[..., C, H, W] float in [-1, 1] -> [..., H, W, C] uint8 as predict.py:124-134 forms it (clamp, inverse
     transform, *255, truncation; BGR -> RGB when C == 3 unless flip_channels says otherwise)."""
