@@ -199,6 +199,8 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0, graph=Tr
     torch.backends.cudnn.allow_tf32 = bool(tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("TAI_CUDNN_BENCHMARK_LIMIT"):           # experiment switch: 0 = let cuDNN try every algorithm
+        torch.backends.cudnn.benchmark_limit = int(os.environ["TAI_CUDNN_BENCHMARK_LIMIT"])
     _lib.load()  # fail loudly here if the CUDA library is missing
 
     key, c, H, W, K, T, F_, B, training = WORKLOADS[workload]

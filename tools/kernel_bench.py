@@ -94,6 +94,15 @@ def main():
                 med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
                 print(json.dumps({"case": "stream", "shape": [B, F, H, W], "kernel": k, "ms_med": med * 1e3,
                                   "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
+        for (N_, C_, H_, W_) in [(64, 64, 128, 128), (64, 128, 64, 64), (64, 256, 32, 32)]:
+            y, gy, bias = torch.randn(N_, C_, H_, W_, device=dev), torch.randn(N_, C_, H_, W_, device=dev), torch.randn(C_, device=dev)
+            el = y.numel()
+            runs = {"bias_act_fwd": (lambda: ops.bias_act_forward_(y, bias, "relu", 0.0), 8.0 * el),
+                    "bias_act_bwd": (lambda: ops.bias_act_backward(gy, y, "relu", 0.0), 12.0 * el)}
+            for k, (fn, by) in runs.items():
+                med, best = timeit(fn, iters=args.iters, warm=args.warm, flush=flush)
+                print(json.dumps({"case": "stream", "shape": [N_, C_, H_, W_], "kernel": k, "ms_med": med * 1e3,
+                                  "gbs": by / med / 1e9, "frac_hbm_6553": by / med / 6553e9}), flush=True)
         for shape in [(32, 5, 1, 128, 128), (8, 3, 3, 240, 320)]:
             x, y = U(*shape), U(*shape)
             one = torch.ones(1, device=dev)

@@ -16,6 +16,7 @@ conv, state = torch.randn(32, 1024, 16, 16, device=dev), torch.randn(32, 512, 16
 gns = torch.randn_like(state)
 a, b = torch.rand(160, 1, 128, 128, device=dev) * 2 - 1, torch.rand(160, 1, 128, 128, device=dev) * 2 - 1
 one = torch.ones(1, device=dev)
+bias, gy = torch.randn(64, device=dev), torch.randn(64, 64, 128, 128, device=dev)
 for _ in range(3):
     flush.zero_()
     ops.upsample_bilinear2x_backward(g)
@@ -28,4 +29,7 @@ for _ in range(3):
     ops.maxpool2x2_backward(out, code, 2 * H, 2 * W)
     ops.l2_gdl_loss_forward(a, b)
     ops.l2_gdl_loss_backward(a, b, one, one)
+    y = torch.randn(64, 64, 128, 128, device=dev)
+    ops.bias_act_forward_(y, bias, "relu", 0.0)
+    ops.bias_act_backward(gy, y, "relu", 0.0)
 torch.cuda.synchronize()
