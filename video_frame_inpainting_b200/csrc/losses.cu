@@ -278,14 +278,12 @@ extern "C" int l2_gdl_loss_forward_b200(const float *pred, const float *target, 
     TAI_REQUIRE(bx < (1LL << 31) && by < 65536, TAI_ERR_TOO_LARGE, "l2_gdl_loss_forward_b200: grid too large");
     const double n_mse = (double)planes * H * W, n_gdl = (double)planes * (H - 1) * (W - 1);
     float2 *partials = reinterpret_cast<float2 *>(workspace);
-    {
-        TimingScope ts("l2_gdl_fwd", st, 0.0, 8.0 * n_mse);  // read the prediction and the target once
-        if (v4)
-            l2_gdl_fwd_kernel<4><<<dim3((unsigned)bx, (unsigned)by), LS_NT, 0, st>>>(pred, target, (long)planes, H, W, add, mul, R, partials);
-        else
-            l2_gdl_fwd_kernel<1><<<dim3((unsigned)bx, (unsigned)by), LS_NT, 0, st>>>(pred, target, (long)planes, H, W, add, mul, R, partials);
-        rc = check_launch("l2_gdl_fwd_kernel");
-    }
+    TimingScope ts("l2_gdl_fwd", st, 0.0, 8.0 * n_mse);  // read the prediction and the target once; both launches
+    if (v4)
+        l2_gdl_fwd_kernel<4><<<dim3((unsigned)bx, (unsigned)by), LS_NT, 0, st>>>(pred, target, (long)planes, H, W, add, mul, R, partials);
+    else
+        l2_gdl_fwd_kernel<1><<<dim3((unsigned)bx, (unsigned)by), LS_NT, 0, st>>>(pred, target, (long)planes, H, W, add, mul, R, partials);
+    rc = check_launch("l2_gdl_fwd_kernel");
     if (rc != TAI_OK) return rc;
     l2_gdl_finalize_kernel<<<1, LS_NT, 0, st>>>(partials, (long)(bx * by), 1.0 / n_mse, 1.0 / n_gdl, out2);
     return check_launch("l2_gdl_finalize_kernel");
