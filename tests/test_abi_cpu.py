@@ -63,3 +63,33 @@ def test_operator_keeps_reference_cpu_behaviour():
         ops.convlstm_gates_forward(torch.randn(1, 8, 2, 2), torch.randn(1, 4, 2, 2))
     with pytest.raises(NotImplementedError):
         ops.flow_warp_forward(torch.randn(1, 3, 4, 4), torch.randn(1, 2, 4, 4))
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under video_frame_inpainting_b200/ may import, load or execute
+    anything under oracle/ (a product path through the oracle would void every parity claim)."""
+    pkg = os.path.join(ROOT, "video_frame_inpainting_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|oracle/_ref|oracle\._", text, flags=re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    from video_frame_inpainting_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)
+    assert lib.maxpool2x2_forward_b200(one, one, one, 1, 1, 8, None) == -1          # H < 2
+    assert lib.maxpool2x2_backward_b200(one, None, one, 1, 4, 4, None) == -1        # no code buffer
+    assert lib.l2_gdl_loss_forward_b200(one, one, 1, 4, 4, 1.0, 0.5, one, None, None) == -1   # no workspace
+    assert lib.l2_gdl_loss_workspace_bytes(160, 128, 128) > 0
+    assert lib.bias_act_forward_b200(one, one, 1, 1, 4, 7, 0.0, None) == -1         # unknown activation
+    assert lib.bias_act_backward_b200(one, None, one, one, one, 1, 1, 4, 1, 0.0, None) == -1  # relu needs the output
+    assert lib.bias_act_backward_workspace_bytes(64, 64) >= 4 * 64
+    assert lib.upsample_bilinear2x_backward_b200(one, one, 1 << 40, 64, 64, None) == -3
+    assert lib.frames_to_uint8_b200(one, one, 0, 3, 4, 4, 1, None) == -1
+    assert lib.l2_normalize_b200(one, one, 0, 1e-12, None) == -1
