@@ -69,46 +69,60 @@ bias_act_bwd_kernel(const float *gout, const float *__restrict__ out, float *gin
     __shared__ float s_red[8];
     const int c = blockIdx.y, chunks = gridDim.x;
     float acc = 0.f;
-    for (int n = blockIdx.x; n < N; n += chunks) {
-        const long base = ((long)n * C + c) * HW;
-        if (VEC) {
-            const float4 *g4 = reinterpret_cast<const float4 *>(gout + base);
-            const float4 *o4 = reinterpret_cast<const float4 *>(out + base);
-            float4 *d4 = reinterpret_cast<float4 *>(gin + base);
-            const int q = HW / 4;
-            int i = threadIdx.x;
-            for (; i + 768 < q; i += 1024) {  // four independent 128-bit pairs per trip: eight loads in flight
-                float4 g[4], o[4];
+    if (VEC) {
+        // The CTA's planes n = k, k + chunks, ... form one flat list of 128-bit items (q per plane); four items,
+        // 1024 apart, are in flight per thread whatever the plane size (a 32 x 32 plane is a single item per
+        // thread: walking plane by plane left one load pair in flight and ran at 61 % of the copy bandwidth).
+        const int q = HW / 4;
+        const int nplanes = (N - (int)blockIdx.x + chunks - 1) / chunks;
+        const int items = nplanes * q;   // < 2^29: the whole tensor has < 2^31 elements
+        auto addr = [&](int i) -> long {
+            const int pl = i / q;
+            return ((long)(blockIdx.x + pl * chunks) * C + c) * q + (i - pl * q);
+        };
+        const float4 *g4 = reinterpret_cast<const float4 *>(gout);
+        const float4 *o4 = reinterpret_cast<const float4 *>(out);
+        float4 *d4 = reinterpret_cast<float4 *>(gin);
+        int i = threadIdx.x;
+        for (; i + 768 < items; i += 1024) {
+            long a[4];
+            float4 g[4], o[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) g[u] = g4[i + 256 * u];
-                if (act != ACT_NONE) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) o[u] = o4[i + 256 * u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        g[u].x = act_grad(g[u].x, o[u].x, act, alpha);
-                        g[u].y = act_grad(g[u].y, o[u].y, act, alpha);
-                        g[u].z = act_grad(g[u].z, o[u].z, act, alpha);
-                        g[u].w = act_grad(g[u].w, o[u].w, act, alpha);
-                        if (write_gin) d4[i + 256 * u] = g[u];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc += (g[u].x + g[u].y) + (g[u].z + g[u].w);
+            for (int u = 0; u < 4; ++u) {
+                a[u] = addr(i + 256 * u);
+                g[u] = g4[a[u]];
             }
-            for (; i < q; i += 256) {
-                float4 g = g4[i];
-                if (act != ACT_NONE) {
-                    const float4 o = o4[i];
-                    g.x = act_grad(g.x, o.x, act, alpha);
-                    g.y = act_grad(g.y, o.y, act, alpha);
-                    g.z = act_grad(g.z, o.z, act, alpha);
-                    g.w = act_grad(g.w, o.w, act, alpha);
-                    if (write_gin) d4[i] = g;
+            if (act != ACT_NONE) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = o4[a[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u].x = act_grad(g[u].x, o[u].x, act, alpha);
+                    g[u].y = act_grad(g[u].y, o[u].y, act, alpha);
+                    g[u].z = act_grad(g[u].z, o[u].z, act, alpha);
+                    g[u].w = act_grad(g[u].w, o[u].w, act, alpha);
+                    if (write_gin) d4[a[u]] = g[u];
                 }
-                acc += (g.x + g.y) + (g.z + g.w);
             }
-        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += (g[u].x + g[u].y) + (g[u].z + g[u].w);
+        }
+        for (; i < items; i += 256) {
+            const long a = addr(i);
+            float4 g = g4[a];
+            if (act != ACT_NONE) {
+                const float4 o = o4[a];
+                g.x = act_grad(g.x, o.x, act, alpha);
+                g.y = act_grad(g.y, o.y, act, alpha);
+                g.z = act_grad(g.z, o.z, act, alpha);
+                g.w = act_grad(g.w, o.w, act, alpha);
+                if (write_gin) d4[a] = g;
+            }
+            acc += (g.x + g.y) + (g.z + g.w);
+        }
+    } else {
+        for (int n = blockIdx.x; n < N; n += chunks) {
+            const long base = ((long)n * C + c) * HW;
             for (int i = threadIdx.x; i < HW; i += 256) {
                 float g = gout[base + i];
                 if (act != ACT_NONE) {

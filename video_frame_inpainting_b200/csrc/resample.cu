@@ -130,6 +130,79 @@ upsample2x_fwd_kernel(const float *__restrict__ in, float *__restrict__ out, int
     }
 }
 
+// Register sliding-window forward (used below W = 64, see the launcher; needs an even W so that the 2W-wide result
+// rows take 128-bit stores): a thread owns FOUR consecutive output columns of one plane and walks R output rows downwards.  The four
+// columns touch at most the input columns cb .. cb+3; their horizontal interpolation is a 4 x 4 weight matrix
+// (two non-zeros per row, formed once per thread), applied once per INPUT row (16 FMAs); an output row is one
+// vertical blend of the two interpolated input rows in registers and one 128-bit store.  The next input row is
+// loaded one step ahead.  ~6 instructions per output element: the shared-memory tile version (stage, horizontal
+// pass, vertical pass, two barriers) spent ~30 and was ISSUE-bound (ncu: issue slots 85 % busy, DRAM at 35 %).
+constexpr int UR_NT = 256;
+
+__global__ void __launch_bounds__(UR_NT)
+upsample2x_fwd_reg_kernel(const float *__restrict__ in, float *__restrict__ out, long planes, int H, int W, float rh, float rw,
+                          int R)
+{
+    const int Ho = 2 * H, Wo = 2 * W, wq = Wo / 4;
+    const int nrb = (Ho + R - 1) / R;
+    const int oy_begin = (int)(blockIdx.x % nrb) * R;       // row block fastest: CTAs sharing input rows run together
+    const long item = (long)(blockIdx.x / nrb) * UR_NT + threadIdx.x;
+    if (item >= planes * wq) return;
+    const long n = item / wq;
+    const int ox0 = 4 * (int)(item - n * wq);
+    const int cb = min(up_tap(ox0, rw, W).i0, max(W - 4, 0));
+    float M[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const Tap2 t = up_tap(ox0 + k, rw, W);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) M[k][j] = (t.i0 == cb + j ? t.w0 : 0.f) + (t.i1 == cb + j ? t.w1 : 0.f);
+    }
+    int col[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) col[j] = min(cb + j, W - 1);
+    const float *p = in + n * H * W;
+    float *o = out + n * Ho * Wo + ox0;
+    auto load_row = [&](int r, float (&v)[4]) {
+        const float *row = p + min(r, H - 1) * W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(row + col[j]);
+    };
+    auto interp = [&](const float (&v)[4], float (&h)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a = M[k][0] * v[0];
+            a = fmaf(M[k][1], v[1], a);
+            a = fmaf(M[k][2], v[2], a);
+            h[k] = fmaf(M[k][3], v[3], a);
+        }
+    };
+    int lo = up_tap(oy_begin, rh, H).i0;   // input row held in h0; h1 holds row min(lo + 1, H - 1)
+    float h0[4], h1[4], v[4], vn[4];
+    load_row(lo, v);
+    interp(v, h0);
+    load_row(lo + 1, v);
+    interp(v, h1);
+    load_row(lo + 2, vn);                  // one input row ahead
+    const int oy_end = min(Ho, oy_begin + R);
+    for (int oy = oy_begin; oy < oy_end; ++oy) {
+        const Tap2 t = up_tap(oy, rh, H);
+        if (t.i0 != lo) {                  // uniform over the CTA; the ratio is < 1/2, so i0 advances by at most one
+            lo = t.i0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h0[k] = h1[k];
+            interp(vn, h1);
+            load_row(lo + 2, vn);
+        }
+        float4 r;
+        r.x = t.w0 * h0[0] + t.w1 * h1[0];
+        r.y = t.w0 * h0[1] + t.w1 * h1[1];
+        r.z = t.w0 * h0[2] + t.w1 * h1[2];
+        r.w = t.w0 * h0[3] + t.w1 * h1[3];
+        *reinterpret_cast<float4 *>(o + (long)oy * Wo) = r;
+    }
+}
+
 // ---- adjoint ----------------------------------------------------------------------------------------
 // Evaluated as a gather (deterministic, no atomics): input pixel (y, x) collects every output pixel whose
 // two taps per axis include it.  With ratio = (in-1)/(2in-1) < 1/2 those are among 2y-2 .. 2y+3.
@@ -474,10 +547,22 @@ extern "C" int upsample_bilinear2x_forward_b200(const float *in, float *out, lon
     const long long blocks = N * tiles_y * tiles_x;
     TAI_REQUIRE(blocks < (1LL << 31), TAI_ERR_TOO_LARGE, "upsample_bilinear2x_forward_b200: too many tiles");
     TimingScope ts("upsample2x_fwd", st, 0.0, 4.0 * (out_el + out_el / 4));  // read the input once, write the result
-    if ((W % 2) == 0 && aligned16(out, out))
+    // measured (B200, us): [32,64,64,64] tile 38.9 / register 49.2; [32,32,64,64] 23.3 / 28.8; [8,64,120,160] 55.1 / 53.3;
+    // [32,128,32,32] 38.9 / 29.7 -- the 128-column tile wastes half its threads below W = 64, the register walk is
+    // latency-bound on large planes: pick by width
+    if ((W % 2) == 0 && W < 64 && aligned16(out, out)) {
+        const long planes = (long)N;
+        const int wq = W / 2;                  // threads per output row
+        int R = 32;                            // output rows per thread; shorter walks when the tensor would not fill the chip
+        while (R > 8 && planes * wq * ceil_div(2 * H, R) < (long)sm_count() * 1024) R /= 2;
+        const long long bx = ((planes * wq + UR_NT - 1) / UR_NT) * ceil_div(2 * H, R);
+        TAI_REQUIRE(bx < (1LL << 31), TAI_ERR_TOO_LARGE, "upsample_bilinear2x_forward_b200: grid too large");
+        upsample2x_fwd_reg_kernel<<<(unsigned)bx, UR_NT, 0, st>>>(in, out, planes, H, W, rh, rw, R);
+    } else if ((W % 2) == 0 && aligned16(out, out)) {
         upsample2x_fwd_kernel<true><<<(unsigned)blocks, UF_NT, 0, st>>>(in, out, H, W, rh, rw, tiles_y, tiles_x);
-    else
+    } else {
         upsample2x_fwd_kernel<false><<<(unsigned)blocks, UF_NT, 0, st>>>(in, out, H, W, rh, rw, tiles_y, tiles_x);
+    }
     return check_launch("upsample2x_fwd_kernel");
 }
 
