@@ -223,3 +223,29 @@ def test_gpu_slomo_matches_reference_classes_golden(cuda):
     out_t['pred'].pow(2).mean().backward()
     name = str(z['s_grad_name'][0])
     assert O.rel_err(dict(model.named_parameters())[name].grad.cpu().numpy(), z['s_grad']) < 2e-2
+
+
+def test_slomo_training_environment_step(cuda):
+    """Super SloMo training step (environments.py:523-620) on this library's warp / loss kernels: the step runs,
+    every loss term is finite, parameters move, and the kernel-route smoothness term equals the reference's
+    GDL(flow, 0) spelled with torch ops."""
+    from video_frame_inpainting_b200.environments.environments import SloMoTrainingEnvironment
+    from video_frame_inpainting_b200.losses.losses import GDL
+    _strict_fp32()
+    torch.manual_seed(0)
+    env = SloMoTrainingEnvironment(SloMoFillInModel(4, 3), "/tmp/tai_b200_test", "slomo", 1e-4, 0.5, 2, 2, 2, (0, 0),
+                                   0.8, 0.005, 0.4, 1.0, 100, 0.1)
+    env.K, env.T, env.F = 2, 2, 2
+    env.train()
+    clip = torch.rand(2, 6, 3, 32, 64) * 2 - 1
+    before = [p.detach().clone() for p in env.generator.parameters()]
+    env.set_train_inputs(clip[:, :2], clip[:, 4:], clip[:, 2:4])
+    env.forward_train()
+    env.optimize_parameters()
+    errs = env.get_current_errors()
+    assert set(errs) >= {'G_loss', 'reconstruction_loss', 'perceptual_loss', 'warping_loss', 'smooth_loss'}
+    assert all(np.isfinite(v) for v in errs.values()), errs
+    assert sum(int(not torch.equal(a, b)) for a, b in zip(before, env.generator.parameters())) > 50
+    flow = env.gen_output['F_0_1'].detach()
+    ref = GDL()(flow, torch.zeros_like(flow)).item()
+    assert abs(env._smoothness(flow).item() - ref) <= 1e-5 * abs(ref)

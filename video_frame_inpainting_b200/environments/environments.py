@@ -2,7 +2,8 @@
 
 Restates ``src/environments/environments.py`` of the reference for torch 2 -- the classes on the TAI path
 only (``BaseVideoFillInEnvironment`` :64-119, ``BaseTrainingEnvironment`` :122-259,
-``L2GDLDiscTrainingEnvironment`` :262-397, ``TAITrainingEnvironment`` :415-485) with the same method
+``L2GDLDiscTrainingEnvironment`` :262-397, ``TAITrainingEnvironment`` :415-485, ``SloMoTrainingEnvironment``
+:523-620) with the same method
 names, loss composition and checkpoint dictionary.  Differences, all on the host side:
 
 * ``Variable`` / ``volatile`` / ``.cuda(async=True)`` (a SyntaxError on Python 3, environments.py:94)
@@ -19,6 +20,7 @@ import os
 import numpy as np
 import torch
 
+from .. import ops
 from ..discriminators.SNDiscriminator import SNDiscriminator
 from ..losses.losses import GDL, L2GDLLoss
 from ..parallel import FlatGradAllReducer, broadcast_module
@@ -291,3 +293,73 @@ class TAITrainingEnvironment(L2GDLDiscTrainingEnvironment):
         errors.update(G_Lp_forward=float(self.Lp_forward.detach()), G_gdl_forward=float(self.gdl_forward.detach()),
                       G_Lp_backward=float(self.Lp_backward.detach()), G_gdl_backward=float(self.gdl_backward.detach()))
         return errors
+
+
+class SloMoTrainingEnvironment(BaseTrainingEnvironment):
+    """Super SloMo training step: reconstruction (L1) + perceptual (VGG-16 conv4_3 features, MSE) + warping (L1 of
+    six-plus-2T backward warps) + smoothness (GDL of the two flows against zero)   (environments.py:523-620).
+
+    On this library's kernels: every warp goes through ``FlowWarper`` (``flow_warp_{forward,backward}_b200``, the
+    reference builds a meshgrid on the host and calls ``grid_sample`` per warp, slomo.py:265-286) and the two
+    smoothness terms through the fused MSE + GDL kernel with an identity transform (``add = 0, mul = 1``; its MSE
+    output is unused).  ``vgg16_state_dict``: the reference loads torchvision's ImageNet weights
+    (``vgg16(pretrained=True)``, environments.py:532); there is no network here, so the caller passes the
+    state_dict (or None: random features -- enough to exercise and time the step, not to train a model)."""
+
+    def __init__(self, fill_in_model, checkpoints_dir, name, lr, beta1, max_K, max_T, max_F, padding_size, lambda_r,
+                 lambda_p, lambda_w, lambda_s, lr_decay_count, lr_decay_rate, vgg16_state_dict=None):
+        super(SloMoTrainingEnvironment, self).__init__(fill_in_model, checkpoints_dir, name, lr, beta1, max_K, max_T,
+                                                       max_F, padding_size)
+        import torchvision
+        from ..models.slomo.slomo import FlowWarper
+        self.l1_loss = torch.nn.L1Loss()
+        self.MSE_loss = torch.nn.MSELoss()
+        self.gdl = GDL()
+        vgg16 = torchvision.models.vgg16(weights=None)
+        if vgg16_state_dict is not None:
+            vgg16.load_state_dict(vgg16_state_dict)
+        self.vgg16_conv = torch.nn.Sequential(*list(vgg16.features.children())[:22]).cuda()   # up to conv4_3 + ReLU
+        for param in self.vgg16_conv.parameters():
+            param.requires_grad = False
+        self.warper = FlowWarper()
+        self.lambda_r, self.lambda_p, self.lambda_w, self.lambda_s = lambda_r, lambda_p, lambda_w, lambda_s
+        self.lr_decay_count, self.lr_decay_rate, self.lr = lr_decay_count, lr_decay_rate, lr
+
+    def _smoothness(self, flow):
+        # GDL(flow, 0) (environments.py:589-590) through the fused loss kernel: identity transform, GDL output
+        return ops.l2_gdl_loss(flow.contiguous(), torch.zeros_like(flow), 0.0, 1.0)[1]
+
+    def compute_loss_G(self):
+        super(SloMoTrainingEnvironment, self).compute_loss_G()
+        B, T, c_dim, H, W = self.gt_middle_frames.shape
+        I0 = self.preceding_frames[:, -1].contiguous()
+        I1 = self.following_frames[:, 0].contiguous()
+        out = self.gen_output
+        pred, F_0_1, F_1_0 = out['pred'], out['F_0_1'], out['F_1_0']
+        gt = self.gt_middle_frames
+        self.reconstruction_loss = self.l1_loss(pred, gt)
+        # perceptual loss: the T frames as one batch (the reference loops over t, environments.py:574-581; the
+        # feature extractor is frozen and stateless, so the result is the same)
+        as_rgb = lambda v: (v.expand(B, T, 3, H, W) if c_dim == 1 else v).reshape(B * T, 3, H, W)
+        self.perceptual_loss = self.MSE_loss(self.vgg16_conv(as_rgb(pred)), self.vgg16_conv(as_rgb(gt)).detach())
+        # warping loss (environments.py:584-586)
+        per_t = [self.l1_loss(self.warper(I0, out['F_t_0_collector'][:, i].contiguous()), gt[:, i])
+                 + self.l1_loss(self.warper(I1, out['F_t_1_collector'][:, i].contiguous()), gt[:, i]) for i in range(T)]
+        self.warping_loss = (self.l1_loss(self.warper(I0, F_1_0), I1) + self.l1_loss(self.warper(I1, F_0_1), I0)
+                             + sum(per_t) / len(per_t))
+        self.smooth_loss = self._smoothness(F_1_0) + self._smoothness(F_0_1)
+        self.loss_G = (self.loss_G + self.lambda_r * self.reconstruction_loss + self.lambda_p * self.perceptual_loss
+                       + self.lambda_w * self.warping_loss + self.lambda_s * self.smooth_loss)
+
+    def get_current_errors(self):
+        errors = super(SloMoTrainingEnvironment, self).get_current_errors()
+        errors.update(reconstruction_loss=float(self.reconstruction_loss.detach()),
+                      perceptual_loss=float(self.perceptual_loss.detach()),
+                      warping_loss=float(self.warping_loss.detach()), smooth_loss=float(self.smooth_loss.detach()))
+        return errors
+
+    def optimize_parameters(self):
+        """Learning-rate step decay, then one generator update (environments.py:609-616)."""
+        for param_group in self.optimizer_G.param_groups:
+            param_group['lr'] = self.lr * (self.lr_decay_rate ** (self.total_updates // self.lr_decay_count))
+        super(SloMoTrainingEnvironment, self).optimize_parameters()
