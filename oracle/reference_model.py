@@ -88,9 +88,7 @@ class CpuBilinearUp2(BilinearUp2):
 class CpuTAIMixin(object):
     """Reference formulation of the filter-and-blend tail for TAI and its TWI subclass."""
 
-    def filter_and_blend(self, variableInput1, variableInput2, variableDyn1, variableDyn2, variableCont1,
-                         variableCont2, variableRes, ratio=0, a=0.5, b=0.5):
-        v1, h1, v2, h2 = self.kernel_maps(variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio)
+    def apply_maps(self, variableInput1, variableInput2, v1, h1, v2, h2, a=0.5, b=0.5):
         apply = CpuSeparableConvolution.apply
         dot1 = apply(self.modulePad(variableInput1).contiguous(), v1.contiguous(), h1.contiguous(), self.ks)
         dot2 = apply(self.modulePad(variableInput2).contiguous(), v2.contiguous(), h2.contiguous(), self.ks)

@@ -155,3 +155,35 @@ def test_reference_slomo_classes_golden():
     out['pred'].pow(2).mean().backward()
     name = str(z['s_grad_name'][0])
     assert O.rel_err(dict(model.named_parameters())[name].grad.numpy(), z['s_grad']) < 1e-4
+
+
+@pytest.mark.parametrize("cls", [TAIFillInModel, TimeWeightedInterpolationFillInModel])
+def test_batched_loop_structure_equals_reference_loops_on_cpu(cls):
+    """Host logic of the batching steps (two MC-Net streams as one pass, kernel network once over T*B frames, motion
+    history as one batch) without a GPU: on the CPU port the batched route must reproduce the reference's loop
+    structure (tai.py:77-84, 91-105; mcnet.py:405-409) -- outputs and parameter gradients."""
+    torch.manual_seed(1)
+    m = cls(4, 1, 3, 5, num_block=5, kf_dim=2)
+    m.apply(weights_init)
+    g = torch.Generator().manual_seed(2)
+    for n, p in m.named_parameters():
+        if n.endswith('bias'):
+            p.data.uniform_(-0.1, 0.1, generator=g)
+    m = to_cpu_reference(m)                        # switches every batching flag off
+    mcnet = m.generator
+    pre = torch.rand(2, 4, 1, 32, 32, generator=g) * 2 - 1
+    fol = torch.rand(2, 4, 1, 32, 32, generator=g) * 2 - 1
+    results = []
+    for batched in (False, True):
+        m.batch_streams = m.batch_time = mcnet.batch_history = batched
+        m.zero_grad(set_to_none=True)
+        out = m(3, pre, fol)
+        (out['pred'].pow(2).mean() + out['pred_forward'].mean() + out['pred_backward'].pow(2).mean()).backward()
+        results.append(({k: v.detach().numpy() for k, v in out.items()},
+                        np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().ravel()
+                                        for p in m.parameters()])))
+    for k in results[0][0]:
+        assert O.rel_err(results[1][0][k], results[0][0][k]) < 1e-4, k
+    assert O.rel_err(results[1][1], results[0][1]) < 1e-3
+    m.batch_streams = m.batch_time = mcnet.batch_history = True
+    assert m(2, pre, fol[:, :3])['pred'].shape == (2, 2, 1, 32, 32)      # K != F: separate MC-Net passes

@@ -111,16 +111,15 @@ class TAIFillInModel(nn.Module):
             v1, h1, v2, h2 = self.kernelnet.kernel_maps(cat(forward_dyn), cat(backward_dyn), cat(forward_cont),
                                                         cat(backward_cont), merged_res, ratio=[w[2] for w in weights])
             pf, pb = cat(forward_pred), cat(backward_pred)
-            ks = self.kernelnet.ks
             if len(set((w[0], w[1]) for w in weights)) == 1:
-                pred, dot1, dot2 = ops.tai_blend_sepconv(pf, pb, v1, h1, v2, h2, ks, weights[0][0], weights[0][1])
+                pred, dot1, dot2 = self.kernelnet.apply_maps(pf, pb, v1, h1, v2, h2, weights[0][0], weights[0][1])
                 combination = list(pred.view(T, B, *pred.shape[1:]).unbind(0))
                 outputs_1 = list(dot1.view(T, B, *dot1.shape[1:]).unbind(0))
                 outputs_2 = list(dot2.view(T, B, *dot2.shape[1:]).unbind(0))
             else:
                 for t, (a, b, _) in enumerate(weights):
                     sl = slice(t * B, (t + 1) * B)
-                    pred_t, dot1, dot2 = ops.tai_blend_sepconv(pf[sl], pb[sl], v1[sl], h1[sl], v2[sl], h2[sl], ks, a, b)
+                    pred_t, dot1, dot2 = self.kernelnet.apply_maps(pf[sl], pb[sl], v1[sl], h1[sl], v2[sl], h2[sl], a, b)
                     combination.append(pred_t)
                     outputs_1.append(dot1)
                     outputs_2.append(dot2)
@@ -211,6 +210,11 @@ class TAI(nn.Module):
                          variableCont2, variableRes, ratio=0, a=0.5, b=0.5):
         """Fused tail: (a*Dot1 + b*Dot2, Dot1, Dot2) in one kernel launch (pad + 2 x sepconv + blend)."""
         v1, h1, v2, h2 = self.kernel_maps(variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio)
+        return self.apply_maps(variableInput1, variableInput2, v1, h1, v2, h2, a, b)
+
+    def apply_maps(self, variableInput1, variableInput2, v1, h1, v2, h2, a=0.5, b=0.5):
+        """(a*Dot1 + b*Dot2, Dot1, Dot2) for given kernel maps: replication pad, the two separable convolutions and
+        the blend as one kernel launch (tai.py:229-236 + 105)."""
         return ops.tai_blend_sepconv(variableInput1.contiguous(), variableInput2.contiguous(), v1.contiguous(),
                                      h1.contiguous(), v2.contiguous(), h2.contiguous(), self.ks, a, b)
 
