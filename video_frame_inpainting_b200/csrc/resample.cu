@@ -256,7 +256,6 @@ __device__ __forceinline__ void up_adj_reduce_x(const float2 (&v)[4], const floa
 }
 
 // needs W even, W >= 4 and 8 B-aligned tensors
-template <bool PIPE>
 __global__ void __launch_bounds__(UA_NT)
 upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, long planes, int H, int W, float rh, float rw,
                       int R)
@@ -296,23 +295,15 @@ upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, l
         up_adj_reduce_x(v, wx0, wx1, d >= 0 && d < Ho, a0[r], a1[r]);
     }
     const int y_end = min(H, y_begin + R);
-    // two input rows per step = four new gradient rows.  Software-pipelined: the sixteen loads of step s+1 are
-    // issued before the arithmetic of step s, so a warp always has 2 KB of loads in flight.
-    float2 v[4][4];
-    if (PIPE) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y_begin + 2 + r, Ho, Wo, v[r]);
-    }
+    // two input rows per step = four new gradient rows, all sixteen loads first.  (An explicitly software-pipelined
+    // form -- the loads of step s+1 issued before the arithmetic of step s, 80 registers, 3 CTAs/SM -- measured
+    // 49 / 33 / 53 us against 46 / 29 / 55 us for this one (48 registers, 5 CTAs/SM) at [32,64,64,64] /
+    // [32,128,32,32] / [8,64,120,160]; rows per thread 8 / 16 / 32 are within 10 % of each other.)
 #pragma unroll 1
     for (int y = y_begin; y < y_end; y += 2) {
-        float2 vn[4][4];
-        if (PIPE) {
+        float2 v[4][4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y + 6 + r, Ho, Wo, vn[r]);  // clamped: never out of bounds
-        } else {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y + 2 + r, Ho, Wo, v[r]);
-        }
+        for (int r = 0; r < 4; ++r) up_adj_load_row(pc, 2 * y + 2 + r, Ho, Wo, v[r]);
         float t0[4], t1[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) up_adj_reduce_x(v[r], wx0, wx1, 2 * y + 2 + r < Ho, t0[r], t1[r]);
@@ -339,12 +330,6 @@ upsample2x_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, l
         for (int r = 0; r < 4; ++r) {
             a0[r] = t0[r];
             a1[r] = t1[r];
-        }
-        if (PIPE) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[r][k] = vn[r][k];
         }
     }
 }
@@ -583,10 +568,7 @@ extern "C" int upsample_bilinear2x_backward_b200(const float *grad_out, float *g
         const long long bx = ((planes * wp + UA_NT - 1) / UA_NT) * ceil_div(H, R);
         TAI_REQUIRE(bx < (1LL << 31), TAI_ERR_TOO_LARGE, "upsample_bilinear2x_backward_b200: grid too large");
         const unsigned grid = (unsigned)bx;
-        // measured (B200, [32,64,64,64] / [32,128,32,32] / [8,64,120,160]): explicit software pipelining of the
-        // sixteen loads (80 registers, 3 CTAs/SM) 49 / 33 / 53 us, plain form (48 registers, 5 CTAs/SM) 46 / 29 / 55 us;
-        // rows per thread 8 / 16 / 32 within 10 % of each other
-        upsample2x_bwd_kernel<false><<<grid, UA_NT, 0, st>>>(grad_out, grad_in, planes, H, W, rh, rw, R);
+        upsample2x_bwd_kernel<<<grid, UA_NT, 0, st>>>(grad_out, grad_in, planes, H, W, rh, rw, R);
     } else {
         upsample2x_bwd_generic_kernel<<<resample_grid(in_el, 256), 256, 0, st>>>(grad_out, grad_in, in_el, H, W, rh, rw);
     }
