@@ -187,3 +187,17 @@ def test_batched_loop_structure_equals_reference_loops_on_cpu(cls):
     assert O.rel_err(results[1][1], results[0][1]) < 1e-3
     m.batch_streams = m.batch_time = mcnet.batch_history = True
     assert m(2, pre, fol[:, :3])['pred'].shape == (2, 2, 1, 32, 32)      # K != F: separate MC-Net passes
+
+
+def test_fused_sequential_keeps_keys_and_cpu_route():
+    """FusedSequential is nn.Sequential for state_dict purposes (the reference's keys) and evaluates CPU tensors with
+    the plain children -- the route the CPU port of the reference model takes."""
+    import torch.nn as nn
+    from video_frame_inpainting_b200.models.layers import FusedSequential
+    torch.manual_seed(0)
+    mods = [nn.Conv2d(2, 4, 3, padding=1), nn.ReLU(), nn.ConvTranspose2d(4, 3, 3, padding=1), nn.LeakyReLU(0.1),
+            nn.Conv2d(3, 1, 1)]
+    plain, fused = nn.Sequential(*mods), FusedSequential(*mods)
+    assert list(plain.state_dict().keys()) == list(fused.state_dict().keys())
+    x = torch.randn(2, 2, 8, 10)
+    assert torch.equal(plain(x), fused(x))
