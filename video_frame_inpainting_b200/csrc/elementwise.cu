@@ -251,11 +251,6 @@ __device__ __forceinline__ WarpCoord warp_coord(int x, int y, float u, float v, 
     return c;
 }
 
-__device__ __forceinline__ float tap(const float *__restrict__ img, int y, int x, int H, int W)
-{
-    return (x >= 0 && y >= 0 && x < W && y < H) ? __ldg(img + (long)y * W + x) : 0.f;
-}
-
 // The four taps of one sample point: offset of the north-west tap, validity of each tap (zero padding) and the
 // bilinear weights -- formed once per pixel and reused for every channel.
 struct Taps {
@@ -310,46 +305,46 @@ warp_fwd_kernel(const float *__restrict__ img, const float *__restrict__ uv, flo
     }
 }
 
-__device__ __forceinline__ void scatter(float *img, int y, int x, int H, int W, float val)
-{
-    if (x >= 0 && y >= 0 && x < W && y < H) atomicAdd(img + (long)y * W + x, val);
-}
-
+// Adjoint of the warp: image gradient scattered with red.global (the destination is zeroed by the launcher; the
+// summation order of colliding taps is run-dependent), flow gradient written directly.  Tap offsets / validity /
+// weights once per pixel, channel loop unrolled for C = 1 / 3 (CT == 0: runtime channel count).
+template <int CT>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float *__restrict__ img, const float *__restrict__ uv, const float *__restrict__ gout,
                 float *__restrict__ gimg, float *__restrict__ guv, int B, int C, const WarpGeom geom)
 {
     const int H = geom.H, W = geom.W;
-    const long hw = (long)H * W;
-    const long n = (long)B * hw;
+    const int hw = H * W;
+    const int n = B * hw;
     const float sx = (float)(W - 1) / (float)W, sy = (float)(H - 1) / (float)H;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
-        const int x = idx % W;
-        const int y = (idx / W) % H;
-        const long b = idx / hw;
-        const long pix = (long)y * W + x;
-        const WarpCoord c = warp_coord(x, y, __ldg(uv + (b * 2) * hw + pix), __ldg(uv + (b * 2 + 1) * hw + pix), geom);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx / hw, pix = idx - b * hw;
+        const int y = pix / W, x = pix - y * W;
+        const float *fl = uv + (long)b * 2 * hw + pix;
+        const WarpCoord c = warp_coord(x, y, __ldg(fl), __ldg(fl + hw), geom);
+        const Taps t = make_taps(c, H, W);
         const float x1 = (float)(c.x0 + 1), y1 = (float)(c.y0 + 1), x0 = (float)c.x0, y0 = (float)c.y0;
         const float ax = x1 - c.ix, bx = c.ix - x0, ay = y1 - c.iy, by = c.iy - y0;
         float gx = 0.f, gy = 0.f;
-        for (int ch = 0; ch < C; ++ch) {
-            const float *im = img + (b * C + ch) * hw;
-            const float g = __ldg(gout + (b * C + ch) * hw + pix);
-            const float nw = tap(im, c.y0, c.x0, H, W), ne = tap(im, c.y0, c.x0 + 1, H, W);
-            const float sw = tap(im, c.y0 + 1, c.x0, H, W), se = tap(im, c.y0 + 1, c.x0 + 1, H, W);
+        const long base = (long)b * C * hw;
+        TAI_CH_LOOP(CT, C) {
+            const float *p = img + base + (long)ch * hw + t.o;
+            const float g = __ldg(gout + base + (long)ch * hw + pix);
+            const float nw = t.v00 ? __ldg(p) : 0.f, ne = t.v01 ? __ldg(p + 1) : 0.f;
+            const float sw = t.v10 ? __ldg(p + W) : 0.f, se = t.v11 ? __ldg(p + W + 1) : 0.f;
             gx += g * ((ne - nw) * ay + (se - sw) * by);
             gy += g * ((sw - nw) * ax + (se - ne) * bx);
             if (gimg) {
-                float *gi = gimg + (b * C + ch) * hw;
-                scatter(gi, c.y0, c.x0, H, W, g * ax * ay);
-                scatter(gi, c.y0, c.x0 + 1, H, W, g * bx * ay);
-                scatter(gi, c.y0 + 1, c.x0, H, W, g * ax * by);
-                scatter(gi, c.y0 + 1, c.x0 + 1, H, W, g * bx * by);
+                float *gi = gimg + base + (long)ch * hw + t.o;
+                if (t.v00) atomicAdd(gi, g * ax * ay);
+                if (t.v01) atomicAdd(gi + 1, g * bx * ay);
+                if (t.v10) atomicAdd(gi + W, g * ax * by);
+                if (t.v11) atomicAdd(gi + W + 1, g * bx * by);
             }
         }
         if (guv) {
-            guv[(b * 2) * hw + pix] = gx * sx;
-            guv[(b * 2 + 1) * hw + pix] = gy * sy;
+            guv[(long)b * 2 * hw + pix] = gx * sx;
+            guv[(long)b * 2 * hw + hw + pix] = gy * sy;
         }
     }
 }
@@ -587,7 +582,14 @@ extern "C" int flow_warp_backward_b200(const float *img, const float *uv, const 
         TAI_REQUIRE(e == cudaSuccess, TAI_ERR_CUDA, "flow_warp_backward_b200: memset: %s", cudaGetErrorString(e));
     }
     TimingScope ts("warp_bwd", st, 0.0, 4.0 * (4.0 + 3.0 * C) * B * H * W);
-    warp_bwd_kernel<<<stream_grid((long)B * H * W, 256), 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, warp_geom(H, W));
+    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const WarpGeom g = warp_geom(H, W);
+    if (C == 3)
+        warp_bwd_kernel<3><<<grid, 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, g);
+    else if (C == 1)
+        warp_bwd_kernel<1><<<grid, 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, g);
+    else
+        warp_bwd_kernel<0><<<grid, 256, 0, st>>>(img, uv, grad_out, g_img, g_uv, B, C, g);
     return check_launch("warp_bwd_kernel");
 }
 
