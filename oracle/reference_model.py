@@ -19,7 +19,8 @@ Parity status: PINNED for the TAI model composition -- tests/golden/tai_model_re
 outputs and gradients produced by the reference's own TAIFillInModel / MCNet / TAI classes (imported unmodified by
 tests/golden/make_model_golden.py; shims listed there) and tests/test_models_cpu.py checks this port against it
 (1e-5 outputs, 1e-4 gradients, strict state_dict load); the same for SloMoFillInModel (slomo.py).  The training step
-(environments.py is a SyntaxError under Python 3) and the SN discriminator are restated from the source only.
+(environments.py is a SyntaxError under Python 3) is restated from the source only; the SN discriminator it uses
+(the product's torch module) is pinned on the reference's own SNDiscriminator classes by the same fixture.
 
 Used by bench.py (``cpu_baseline`` and ``--impl reference``) and by tests as an end-to-end checker of
 the GPU model.  Never imported by the product package.

@@ -164,6 +164,43 @@ def main():
     out['s_grad'] = dict(sm.named_parameters())[first].grad.numpy()
     print('slomo params', sum(p.numel() for p in sm.parameters()), 'pred rms', float(res['pred'].detach().pow(2).mean().sqrt()),
           'flow rms', float(res['F_0_1'].detach().pow(2).mean().sqrt()))
+    # Spectral-norm discriminator (src/discriminators/SNDiscriminator.py): window slicing, one power-iteration update
+    # per SN layer and window with the in-place division of weight.data, u carried between calls.  The reference
+    # draws the initial u from the global RNG on first use; the fixture presets it on both sides (both
+    # implementations take a given u as it is, SNDiscriminator.py:16-20).  Shim: torch >= 1.x's _ConvNd.__init__
+    # takes a padding_mode argument that SNConv2d (SNDiscriminator.py:60-61) does not pass.
+    from torch.nn.modules import conv as conv_mod
+    convnd_init = conv_mod._ConvNd.__init__
+
+    def convnd_init_compat(self, *args, **kwargs):
+        if len(args) == 10 and 'padding_mode' not in kwargs:
+            args = args + ('zeros',)
+        convnd_init(self, *args, **kwargs)
+    conv_mod._ConvNd.__init__ = convnd_init_compat
+    import src.discriminators.SNDiscriminator as ref_disc
+    torch.manual_seed(400)
+    disc = ref_disc.SNDiscriminator((32, 32), 1, 3, 4, 3)
+    disc.apply(ref_util.weights_init)
+    g = torch.Generator().manual_seed(401)
+    sn_layers = [m for m in disc.modules() if hasattr(m, 'Ip')]
+    for i, m in enumerate(sn_layers):
+        m.u = torch.randn(1, m.weight.size(0), generator=g)
+        out['d_u%d' % i] = m.u.numpy().copy()
+    names = []
+    for name, v in disc.state_dict().items():
+        names.append(name)
+        out['d_sd_' + name] = v.numpy().copy()          # weights BEFORE the first call (forward normalises in place)
+    out['d_sd_names'] = np.array(names)
+    video = torch.rand(2, 6, 1, 32, 32, generator=g) * 2 - 1
+    out['d_video'] = video.numpy()
+    out['d_logits_call1'] = disc(video).detach().numpy()
+    logits2 = disc(video)
+    out['d_logits_call2'] = logits2.detach().numpy()
+    logits2.sum().backward()
+    out['d_weight0_after'] = disc.conv_layers[0].weight.detach().numpy().copy()
+    out['d_grad_weight0'] = disc.conv_layers[0].weight.grad.numpy().copy()
+    out['d_grad_linear'] = disc.linear_layer.weight.grad.numpy().copy()
+    print('discriminator params', sum(p.numel() for p in disc.parameters()), 'logits', out['d_logits_call2'].shape)
     out['n'] = np.int64(len(cases))
     path = os.path.join(HERE, 'tai_model_ref.npz')
     np.savez_compressed(path, **out)

@@ -201,3 +201,27 @@ def test_fused_sequential_keeps_keys_and_cpu_route():
     assert list(plain.state_dict().keys()) == list(fused.state_dict().keys())
     x = torch.randn(2, 2, 8, 10)
     assert torch.equal(plain(x), fused(x))
+
+
+def test_reference_sn_discriminator_golden():
+    """The spectral-norm discriminator against the reference's own SNDiscriminator classes (tests/golden/
+    tai_model_ref.npz, 'd_*'): strict state_dict load, logits of two consecutive calls (the in-place weight
+    normalisation and the carried u), the normalised weight and gradients.  The initial u vectors come from the
+    fixture (the reference draws them from the global RNG)."""
+    import os
+    from video_frame_inpainting_b200.discriminators.SNDiscriminator import SNDiscriminator
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    sd = {str(n): torch.from_numpy(z['d_sd_' + str(n)]) for n in z['d_sd_names']}
+    disc = SNDiscriminator((32, 32), 1, 3, 4, 3)
+    assert list(disc.state_dict().keys()) == list(sd.keys())
+    disc.load_state_dict(sd, strict=True)
+    for i, m in enumerate([m for m in disc.modules() if hasattr(m, 'Ip')]):
+        m.u = torch.from_numpy(z['d_u%d' % i])
+    video = torch.from_numpy(z['d_video'])
+    assert O.rel_err(disc(video).detach().numpy(), z['d_logits_call1']) < 1e-5
+    logits2 = disc(video)
+    assert O.rel_err(logits2.detach().numpy(), z['d_logits_call2']) < 1e-5
+    logits2.sum().backward()
+    assert O.rel_err(disc.conv_layers[0].weight.detach().numpy(), z['d_weight0_after']) < 1e-5
+    assert O.rel_err(disc.conv_layers[0].weight.grad.numpy(), z['d_grad_weight0']) < 1e-4
+    assert O.rel_err(disc.linear_layer.weight.grad.numpy(), z['d_grad_linear']) < 1e-4
