@@ -151,7 +151,10 @@ def to_cpu_reference(model):
 
 class CpuTAITrainingStep(object):
     """The TAI training step (environments.py:222-228, 326-379, 429-453) on CPU tensors: same losses,
-    optimisers and update order as video_frame_inpainting_b200.environments.TAITrainingEnvironment."""
+    optimisers and update order as video_frame_inpainting_b200.environments.TAITrainingEnvironment.
+    Pinned: tests/golden/tai_step_ref.npz holds one step of the reference's own TAITrainingEnvironment
+    (tests/golden/make_step_golden.py); tests/test_models_cpu.py checks every loss term and the updated
+    parameters of this port against it."""
 
     def __init__(self, generator, image_size, c_dim, K, T, F_, alpha=1.0, beta=0.02, lr=1e-4, beta1=0.5, df_dim=64,
                  Ip=3, disc_t=3):
@@ -184,19 +187,26 @@ class CpuTAITrainingStep(object):
         gt = self._tm01(gt_middle)
         self.optimizer_G.zero_grad()
         loss = 0
-        for key in ('pred', 'pred_forward', 'pred_backward'):
+        self.terms = {}
+        for key, tag in (('pred', ''), ('pred_forward', '_forward'), ('pred_backward', '_backward')):
             x = self._tm01(out[key])
-            loss = loss + self.alpha * (self.mse(x, gt) + self.gdl(x, gt))
+            lp, gdl = self.mse(x, gt), self.gdl(x, gt)
+            self.terms['Lp' + tag], self.terms['gdl' + tag] = float(lp.detach()), float(gdl.detach())
+            loss = loss + self.alpha * (lp + gdl)
         video = torch.cat([preceding, out['pred'], following], dim=1)
         h = self.discriminator(video)
-        loss = loss + self.beta * self.bce(h, torch.ones_like(h))
+        l_gan = self.bce(h, torch.ones_like(h))
+        loss = loss + self.beta * l_gan
         loss.backward()
         self.optimizer_G.step()
         self.optimizer_D.zero_grad()
         h = self.discriminator(video.detach())
         labels = self._fake_labels().view(1, -1).expand(h.size(0), -1)
         h_real = self.discriminator(torch.cat([preceding, gt_middle, following], dim=1))
-        loss_d = self.bce(h, labels) + self.bce(h_real, torch.ones_like(h_real))
+        l_fake, l_real = self.bce(h, labels), self.bce(h_real, torch.ones_like(h_real))
+        loss_d = l_fake + l_real
         loss_d.backward()
         self.optimizer_D.step()
+        self.terms.update(L_GAN=float(l_gan.detach()), loss_G=float(loss.detach()), loss_d_fake=float(l_fake.detach()),
+                          loss_d_real=float(l_real.detach()), loss_D=float(loss_d.detach()))
         return float(loss.detach()), float(loss_d.detach())

@@ -225,3 +225,43 @@ def test_reference_sn_discriminator_golden():
     assert O.rel_err(disc.conv_layers[0].weight.detach().numpy(), z['d_weight0_after']) < 1e-5
     assert O.rel_err(disc.conv_layers[0].weight.grad.numpy(), z['d_grad_weight0']) < 1e-4
     assert O.rel_err(disc.linear_layer.weight.grad.numpy(), z['d_grad_linear']) < 1e-4
+
+
+def _load_step_golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_step_ref.npz"))
+    cfg = {k[4:]: float(z[k]) for k in z.files if k.startswith('cfg_')}
+    ints = {k: int(cfg[k]) for k in ('gf_dim', 'c_dim', 'feature_size', 'ks', 'num_block', 'kf_dim', 'K', 'T', 'F_', 'H', 'W',
+                                     'B', 'df_dim', 'Ip', 'disc_t')}
+    gsd = {str(n): torch.from_numpy(z['g_sd_' + str(n)]) for n in z['g_sd_names']}
+    dsd = {str(n): torch.from_numpy(z['d_sd_' + str(n)]) for n in z['d_sd_names']}
+    return z, cfg, ints, gsd, dsd
+
+
+STEP_TERMS = ('Lp', 'gdl', 'L_GAN', 'Lp_forward', 'Lp_backward', 'gdl_forward', 'gdl_backward', 'loss_G', 'loss_d_fake',
+              'loss_d_real', 'loss_D')
+
+
+def test_reference_training_step_golden():
+    """One training step of the reference's OWN TAITrainingEnvironment (tests/golden/tai_step_ref.npz, produced by
+    tests/golden/make_step_golden.py from environments.py with the single token async=True replaced): the CPU port
+    of the step must reproduce all eleven loss terms and the parameters after both Adam updates."""
+    z, cfg, i, gsd, dsd = _load_step_golden()
+    gen = TAIFillInModel(i['gf_dim'], i['c_dim'], i['feature_size'], i['ks'], num_block=i['num_block'], kf_dim=i['kf_dim'])
+    st = CpuTAITrainingStep(gen, (i['H'], i['W']), i['c_dim'], i['K'], i['T'], i['F_'], alpha=cfg['alpha'], beta=cfg['beta'],
+                            lr=cfg['lr'], beta1=cfg['beta1'], df_dim=i['df_dim'], Ip=i['Ip'], disc_t=i['disc_t'])
+    st.generator.load_state_dict(gsd, strict=True)
+    st.discriminator.load_state_dict(dsd, strict=True)
+    for k, m in enumerate([m for m in st.discriminator.modules() if hasattr(m, 'Ip')]):
+        m.u = torch.from_numpy(z['u%d' % k])
+    clip = torch.from_numpy(z['clip'])
+    K, T = i['K'], i['T']
+    st.step(clip[:, :K], clip[:, K + T:], clip[:, K:K + T])
+    for name in STEP_TERMS:
+        ref = float(z['loss_' + name])
+        assert abs(st.terms[name] - ref) <= 1e-5 * abs(ref), (name, st.terms[name], ref)
+    gp, dp = dict(st.generator.named_parameters()), dict(st.discriminator.named_parameters())
+    for n in z['g_after_names']:
+        assert O.rel_err(gp[str(n)].detach().numpy(), z['g_after_' + str(n)]) < 1e-5, n
+    for n in z['d_after_names']:
+        assert O.rel_err(dp[str(n)].detach().numpy(), z['d_after_' + str(n)]) < 1e-5, n

@@ -263,3 +263,35 @@ def test_slomo_training_environment_step(cuda):
     flow = env.gen_output['F_0_1'].detach()
     ref = GDL()(flow, torch.zeros_like(flow)).item()
     assert abs(env._smoothness(flow).item() - ref) <= 1e-5 * abs(ref)
+
+
+def test_training_environment_matches_reference_step_golden(cuda):
+    """The product's TAITrainingEnvironment on the GPU (kernels + batched loop structure + fused losses + bias /
+    activation epilogues) against ONE step of the reference's own TAITrainingEnvironment
+    (tests/golden/tai_step_ref.npz, tests/golden/make_step_golden.py): all eleven loss terms."""
+    import os
+    from video_frame_inpainting_b200.environments.environments import TAITrainingEnvironment
+    _strict_fp32()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_step_ref.npz"))
+    cfg = {k[4:]: float(z[k]) for k in z.files if k.startswith('cfg_')}
+    i = {k: int(v) for k, v in cfg.items() if k not in ('alpha', 'beta', 'lr', 'beta1')}
+    gen = TAIFillInModel(i['gf_dim'], i['c_dim'], i['feature_size'], i['ks'], num_block=i['num_block'], kf_dim=i['kf_dim'])
+    env = TAITrainingEnvironment(gen, "/tmp/tai_b200_test", "golden", (i['H'], i['W']), i['c_dim'], cfg['alpha'],
+                                 cfg['beta'], cfg['lr'], cfg['beta1'], i['df_dim'], i['Ip'], i['disc_t'], i['K'], i['T'],
+                                 i['F_'], (0, 0))
+    env.generator.load_state_dict({str(n): torch.from_numpy(z['g_sd_' + str(n)]) for n in z['g_sd_names']}, strict=True)
+    env.discriminator.load_state_dict({str(n): torch.from_numpy(z['d_sd_' + str(n)]) for n in z['d_sd_names']},
+                                      strict=True)
+    for k, m in enumerate([m for m in env.discriminator.modules() if hasattr(m, 'Ip')]):
+        m.u = torch.from_numpy(z['u%d' % k]).cuda()
+    clip = torch.from_numpy(z['clip'])
+    K, T = i['K'], i['T']
+    env.K, env.T, env.F = i['K'], i['T'], i['F_']
+    env.train()
+    env.set_train_inputs(clip[:, :K], clip[:, K + T:], clip[:, K:K + T])
+    env.forward_train()
+    env.optimize_parameters()
+    for name in ('Lp', 'gdl', 'L_GAN', 'Lp_forward', 'Lp_backward', 'gdl_forward', 'gdl_backward', 'loss_G', 'loss_d_fake',
+                 'loss_d_real', 'loss_D'):
+        got, ref = float(getattr(env, name).detach().reshape(-1)[0]), float(z['loss_' + name])
+        assert abs(got - ref) <= 2e-3 * abs(ref), (name, got, ref)
