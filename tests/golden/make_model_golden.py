@@ -131,6 +131,37 @@ def main():
             out[tag + 'grad_' + n] = params[n].grad.numpy()
         out[tag + 'grad_names'] = np.array(picks)
         print('case', ci, 'params', sum(p.numel() for p in model.parameters()), 'pred rms', float(res['pred'].pow(2).mean().sqrt()))
+    # bi-TWI ablation (src/models/twi/twi.py: time-weighted blend, no time-ratio plane) and the forward-only MC-Net
+    # baseline (src/models/mcnet/mcnet.py: MCNetFillInModel)
+    import src.models.twi.twi as ref_twi
+    import src.models.mcnet.mcnet as ref_mcnet
+    torch.manual_seed(600)
+    extra = {'twi': ref_twi.TimeWeightedInterpolationFillInModel(4, 1, 3, 5, num_block=5, kf_dim=2),
+             'mcnet': ref_mcnet.MCNetFillInModel(4, 3, 3)}
+    g = torch.Generator().manual_seed(601)
+    for tag, em in extra.items():
+        em.apply(ref_util.weights_init)
+        for name, p in em.named_parameters():
+            if name.endswith('bias'):
+                p.data.uniform_(-0.1, 0.1, generator=g)
+        c = 1 if tag == 'twi' else 3
+        pre = torch.rand(2, 3, c, 32, 32, generator=g) * 2 - 1
+        fol = torch.rand(2, 3, c, 32, 32, generator=g) * 2 - 1
+        res = em(3, pre, fol)
+        res['pred'].pow(2).mean().backward()
+        out[tag + '_pre'], out[tag + '_fol'] = pre.numpy(), fol.numpy()
+        for k, v in res.items():
+            out[tag + '_out_' + k] = v.detach().numpy()
+        names = []
+        for name, v in em.state_dict().items():
+            names.append(name)
+            out[tag + '_sd_' + name] = v.numpy()
+        out[tag + '_sd_names'] = np.array(names)
+        first = [n for n, _ in em.named_parameters()][0]
+        out[tag + '_grad_name'] = np.array([first])
+        out[tag + '_grad'] = dict(em.named_parameters())[first].grad.numpy()
+        print(tag, 'params', sum(p.numel() for p in em.parameters()), 'outputs', sorted(res))
+
     # Super SloMo baseline (src/models/slomo/slomo.py): flow combination, warps, refinement, visibility blend, and
     # the reversed time order in which the reference concatenates its predictions (slomo.py:331-340)
     import src.models.slomo.slomo as ref_slomo

@@ -265,3 +265,27 @@ def test_reference_training_step_golden():
         assert O.rel_err(gp[str(n)].detach().numpy(), z['g_after_' + str(n)]) < 1e-5, n
     for n in z['d_after_names']:
         assert O.rel_err(dp[str(n)].detach().numpy(), z['d_after_' + str(n)]) < 1e-5, n
+
+
+@pytest.mark.parametrize("tag", ["twi", "mcnet"])
+def test_reference_twi_and_mcnet_classes_golden(tag):
+    """bi-TWI (src/models/twi/twi.py: per-t blend weights, no time-ratio plane) and the forward-only MC-Net baseline
+    (mcnet.py:301-347) against outputs of the reference's own classes: strict state_dict load, every output, a
+    gradient."""
+    import os
+    from video_frame_inpainting_b200.models.mcnet.mcnet import MCNetFillInModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_model_ref.npz"))
+    sd = {str(n): torch.from_numpy(z[tag + '_sd_' + str(n)]) for n in z[tag + '_sd_names']}
+    model = (TimeWeightedInterpolationFillInModel(4, 1, 3, 5, num_block=5, kf_dim=2) if tag == 'twi'
+             else MCNetFillInModel(4, 3, 3))
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    model = to_cpu_reference(model)
+    out = model(3, torch.from_numpy(z[tag + '_pre']), torch.from_numpy(z[tag + '_fol']))
+    keys = [k[len(tag) + 5:] for k in z.files if k.startswith(tag + '_out_')]
+    assert sorted(out) == sorted(keys)
+    for k in keys:
+        assert O.rel_err(out[k].detach().numpy(), z[tag + '_out_' + k]) < 1e-5, k
+    out['pred'].pow(2).mean().backward()
+    name = str(z[tag + '_grad_name'][0])
+    assert O.rel_err(dict(model.named_parameters())[name].grad.numpy(), z[tag + '_grad']) < 1e-4
