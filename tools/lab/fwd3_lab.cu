@@ -137,9 +137,10 @@ int main(int argc, char **argv)
     p.in[0] = d_in; p.ver[0] = d_v; p.hor[0] = d_h; p.out[0] = d_out;
     p.B = B; p.C = C; p.Ho = Ho; p.Wo = Wo; p.ks = ks;
     printf("shape B=%d C=%d %dx%d ks=%d\n", B, C, Ho, Wo, ks);
+    printf("rows per warp FP=%d, launch bound %d CTAs/SM\n", FP, TAI_FWD_MIN_CTAS);
+    g_ctas_per_sm = 8;   // as many as the occupancy query allows
+    run_variant("v3 occ", p, d_out, ref, flush, flush_bytes);
     g_ctas_per_sm = 3;
     run_variant("v3 x3", p, d_out, ref, flush, flush_bytes);
-    g_ctas_per_sm = 2;
-    run_variant("v3 x2", p, d_out, ref, flush, flush_bytes);
     return 0;
 }

@@ -5,7 +5,14 @@
 
 namespace tai {
 
-constexpr int FP = 8;   // output rows per thread
+// TAI_FP / TAI_FWD_MIN_CTAS: overridable by the lab harnesses (tools/lab) only; the product builds with the defaults.
+#ifndef TAI_FP
+#define TAI_FP 8
+#endif
+#ifndef TAI_FWD_MIN_CTAS
+#define TAI_FWD_MIN_CTAS 3
+#endif
+constexpr int FP = TAI_FP;  // output rows per thread
 constexpr int FNX = 8;  // output columns per warp
 
 template <int I, int N, class F>

@@ -95,7 +95,7 @@ __device__ __forceinline__ void fwd_row_v3(const float *__restrict__ srow, const
 }
 
 template <int KS, int CG, bool PAD, bool DUAL>
-__global__ void __launch_bounds__(128, (CG == 1 ? 3 : 2))
+__global__ void __launch_bounds__(128, (CG == 1 ? TAI_FWD_MIN_CTAS : 2))
 sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
 {
     using Cfg = FwdV3Cfg<KS>;
