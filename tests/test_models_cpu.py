@@ -289,3 +289,27 @@ def test_reference_twi_and_mcnet_classes_golden(tag):
     out['pred'].pow(2).mean().backward()
     name = str(z[tag + '_grad_name'][0])
     assert O.rel_err(dict(model.named_parameters())[name].grad.numpy(), z[tag + '_grad']) < 1e-4
+
+
+def test_training_environment_factory_keeps_reference_signature():
+    """create_training_environment(...) takes the reference's positional arguments in the reference's order
+    (environments.py:24-26) and rejects model families that are out of scope with the reference's error."""
+    import inspect
+    from video_frame_inpainting_b200.environments import environments as E
+    ref_order = ['fill_in_model', 'c_dim', 'checkpoints_dir', 'name', 'max_K', 'max_T', 'max_F', 'image_size', 'alpha',
+                 'beta', 'lr', 'beta1', 'df_dim', 'Ip', 'disc_window_size', 'tf_p_min', 'tf_p_max', 'tf_offset',
+                 'tf_decay', 'padding_size', 'lambda_r', 'lambda_p', 'lambda_w', 'lambda_s', 'lr_decay_count',
+                 'lr_decay_rate']
+    assert list(inspect.signature(E.create_training_environment).parameters)[:len(ref_order)] == ref_order
+    with pytest.raises(RuntimeError, match='unsupported type'):
+        E.create_training_environment(object(), 1, '/tmp', 'x', 2, 2, 2, (32, 32), 1.0, 0.02, 1e-4, 0.5, 8, 3, 3)
+    for cls in ('BaseVideoFillInEnvironment', 'BaseTrainingEnvironment', 'L2GDLDiscTrainingEnvironment',
+                'MCNetTrainingEnvironment', 'TAITrainingEnvironment', 'SloMoTrainingEnvironment'):
+        assert hasattr(E, cls)
+    np.random.seed(0)
+    env = E.MCNetTrainingEnvironment.__new__(E.MCNetTrainingEnvironment)
+    env.max_K, env.max_T, env.max_F = 5, 4, 3
+    for _ in range(50):
+        K, T, F_ = env.sample_KTF(True)
+        assert 2 <= K <= 5 and 1 <= T <= 4 and 1 <= F_ <= 3
+    assert env.sample_KTF(False) == (5, 4, 3)

@@ -28,10 +28,30 @@ from ..util.util import inverse_transform, move_to_devices, weights_init
 
 
 def create_training_environment(fill_in_model, c_dim, checkpoints_dir, name, max_K, max_T, max_F, image_size, alpha,
-                                beta, lr, beta1, df_dim, Ip, disc_window_size, padding_size=(0, 0)):
-    """Factory (environments.py:24-52), TAI-path models only.  Resumes from model_latest.ckpt if present."""
-    env = TAITrainingEnvironment(fill_in_model, checkpoints_dir, name, image_size, c_dim, alpha, beta, lr, beta1,
-                                 df_dim, Ip, disc_window_size, max_K, max_T, max_F, padding_size)
+                                beta, lr, beta1, df_dim, Ip, disc_window_size, tf_p_min=None, tf_p_max=None,
+                                tf_offset=None, tf_decay=None, padding_size=(0, 0), lambda_r=0.8, lambda_p=0.005,
+                                lambda_w=0.4, lambda_s=1.0, lr_decay_count=200, lr_decay_rate=0.1,
+                                vgg16_state_dict=None):
+    """Factory with the reference's argument order (environments.py:24-52): dispatches on the model family -- bi-TAI /
+    bi-TWI -> ``TAITrainingEnvironment``, MC-Net -> ``MCNetTrainingEnvironment``, Super SloMo ->
+    ``SloMoTrainingEnvironment``.  The teacher-forcing arguments belong to the self-attention models (out of scope)
+    and are accepted and ignored.  Resumes from model_latest.ckpt if present."""
+    from ..models.mcnet.mcnet import MCNetFillInModel
+    from ..models.slomo.slomo import SloMoFillInModel
+    from ..models.tai.tai import TAIFillInModel
+    if isinstance(fill_in_model, TAIFillInModel):          # TimeWeightedInterpolationFillInModel derives from it
+        env = TAITrainingEnvironment(fill_in_model, checkpoints_dir, name, image_size, c_dim, alpha, beta, lr, beta1,
+                                     df_dim, Ip, disc_window_size, max_K, max_T, max_F, padding_size)
+    elif isinstance(fill_in_model, MCNetFillInModel):
+        env = MCNetTrainingEnvironment(fill_in_model, checkpoints_dir, name, image_size, c_dim, alpha, beta, lr, beta1,
+                                       df_dim, Ip, disc_window_size, max_K, max_T, max_F, padding_size)
+    elif isinstance(fill_in_model, SloMoFillInModel):
+        env = SloMoTrainingEnvironment(fill_in_model, checkpoints_dir, name, lr, beta1, max_K, max_T, max_F, padding_size,
+                                       lambda_r, lambda_p, lambda_w, lambda_s, lr_decay_count, lr_decay_rate,
+                                       vgg16_state_dict=vgg16_state_dict)
+    else:
+        raise RuntimeError('Tried to create a training environment for object of unsupported type %s'
+                           % type(fill_in_model).__name__)
     if os.path.isfile(os.path.join(checkpoints_dir, name, 'model_latest.ckpt')):
         env.load('model_latest.ckpt')
     return env
@@ -269,6 +289,17 @@ class L2GDLDiscTrainingEnvironment(BaseTrainingEnvironment):
     def train(self):
         super(L2GDLDiscTrainingEnvironment, self).train()
         self.discriminator.train()
+
+
+class MCNetTrainingEnvironment(L2GDLDiscTrainingEnvironment):
+    """L2 + GDL + adversarial step for the forward-only MC-Net baseline (environments.py:398-411): at least two
+    preceding frames (one difference frame) when K, T, F are sampled."""
+
+    def sample_KTF(self, allow_random_sampling):
+        if allow_random_sampling:
+            return (np.random.randint(2, self.max_K + 1), np.random.randint(1, self.max_T + 1),
+                    np.random.randint(1, self.max_F + 1))
+        return self.max_K, self.max_T, self.max_F
 
 
 class TAITrainingEnvironment(L2GDLDiscTrainingEnvironment):
