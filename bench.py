@@ -33,6 +33,12 @@ sys.path.insert(0, ROOT)
 METRIC = "bi-TAI inpainted frames/sec (KTH training step: fwd + bwd + Adam, generator and discriminator)"
 UNIT = "frames/s"
 
+
+def metric_name(workload):
+    if WORKLOADS[workload][8]:
+        return METRIC
+    return "bi-TAI inpainted frames/sec (inference forward pass, %s)" % workload
+
 WORKLOADS = {
     # name: model_key, c_dim, H, W, K, T, F, batch per GPU, training?
     "kth_train_b32": ("TAI_gray", 1, 128, 128, 5, 5, 5, 32, True),
@@ -55,6 +61,22 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="inference workloads: eager launches instead of CUDA-graph replay")
     return ap.parse_args()
+
+
+SEPCONV_KERNELS = ("sepconv_fused_fwd", "sepconv_fwd", "sepconv_bwd_vh", "sepconv_bwd_i")
+WARP_KERNELS = ("slomo_combine_warp", "slomo_refine_blend", "warp_fwd", "warp_bwd")
+HEADLINE_KERNELS = {"kth_train_b32": SEPCONV_KERNELS, "kth_infer_b1": SEPCONV_KERNELS, "ucf_infer_b8": SEPCONV_KERNELS,
+                    "slomo_infer_b8": WARP_KERNELS}
+
+
+def load_traffic(workload):
+    """profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from one
+    `ncu --set full` capture per kernel, at the launch shape of the named workload."""
+    path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if not os.path.isfile(path):
+        return {}
+    with open(path) as f:
+        return json.load(f).get("workloads", {}).get(workload, {})
 
 
 def measured_peaks():
@@ -113,7 +135,18 @@ class ClockSampler(object):
 # CPU port of the reference (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_step_factory(workload, spatial=None):
+def workload_config(workload, B, world, tf32=False, graph=False):
+    """The `config` object of the JSON line: the same dict for the B200 arm and the reference arm."""
+    key, c, H, W, K, T, F_, _, training = WORKLOADS[workload]
+    return {"workload": workload, "model_key": key, "clips_per_gpu": B, "global_clips": B * world,
+            "frame": [c, H, W], "K": K, "T": T, "F": F_, "training": training, "ks": 51,
+            "conv_math": "tf32" if tf32 else "fp32 (cudnn.allow_tf32=False)",
+            "launch": "cuda-graph replay of the forward pass" if graph else "eager",
+            "parallelism": "dp%d (clips sharded, NCCL all-reduce of gradients only)" % world,
+            "l2": "per-step working set (activations, 4 x 107 MB kernel maps per middle frame) >> 126 MB L2"}
+
+
+def cpu_reference_step_factory(workload, spatial=None, clips=1):
     import torch
     from oracle.reference_model import CpuTAITrainingStep, to_cpu_reference
     from video_frame_inpainting_b200.models.create_model import create_model
@@ -124,7 +157,7 @@ def cpu_reference_step_factory(workload, spatial=None):
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(0)
-    clip = torch.rand(1, K + T + F_, c, H, W, generator=g) * 2 - 1
+    clip = torch.rand(clips, K + T + F_, c, H, W, generator=g) * 2 - 1
     pre, mid, fol = clip[:, :K].contiguous(), clip[:, K:K + T].contiguous(), clip[:, K + T:].contiguous()
     if training:
         st = CpuTAITrainingStep(create_model(key), (H, W), c, K, T, F_, alpha=TRAIN_HP["alpha"], beta=TRAIN_HP["beta"],
@@ -139,31 +172,45 @@ def cpu_reference_step_factory(workload, spatial=None):
         def fn():
             with torch.no_grad():
                 return model(T, pre, fol)
-    frames = T
-    sample = "%s: 1 step on 1 clip (batch 1 of the %dx%d workload, %d middle frames), FP32, torch CPU convs + C port of " \
-             "the reference kernels" % ("training" if training else "inference", H, W, T)
+    frames = T * clips
+    sample = "%s: 1 step on %d clip(s) of the %dx%d workload (%d middle frames each), FP32, torch CPU convs + C port " \
+             "of the reference kernels (OpenMP), all host threads" % ("training" if training else "inference", clips,
+                                                                     H, W, T)
     return fn, frames, sample
 
 
+def cpu_clips_for_budget(workload, budget_s, nsteps, cap):
+    """Clips per CPU step such that `nsteps` steps fit `budget_s`: one clip is timed first (after a warm-up),
+    the batch is then sized from it (a larger batch only uses the host cores better)."""
+    fn, _, _ = cpu_reference_step_factory(workload)
+    fn()
+    t0 = time.time()
+    fn()
+    t1 = time.time() - t0
+    clips = int(budget_s / (max(1, nsteps) * max(t1, 1e-3)))
+    return max(1, min(cap, clips)), t1
+
+
 def run_reference(args):
-    """--impl reference: the CPU port, rank 0 only."""
+    """--impl reference: the CPU port, rank 0 only (the other ranks exit 0 without work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation with all host threads
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
-    fn, frames, sample = cpu_reference_step_factory(args.workload)
-    t0 = time.time()
-    fn()
-    first = time.time() - t0
+    B = args.batch or WORKLOADS[args.workload][7]
+    nsteps = args.steps + max(0, args.warmup)
+    # a bounded sample of the workload: as many of the B clips per step as keep the whole run near four minutes
+    clips, t1 = cpu_clips_for_budget(args.workload, 240.0, nsteps, B)
     spatial = None
-    if first * (args.steps + max(0, args.warmup - 1)) > 420.0:  # keep the whole run within a few minutes
+    if t1 * nsteps > 420.0:  # even one clip per step does not fit: crop the frames
         spatial = (64, 64)
-        fn, frames, sample = cpu_reference_step_factory(args.workload, spatial)
-        sample += " [cropped to 64x64: the full-size step took %.1f s]" % first
-        fn()
-    for _ in range(max(0, args.warmup - 1)):
+        clips = 1
+    fn, frames, sample = cpu_reference_step_factory(args.workload, spatial, clips)
+    if spatial:
+        sample += " [cropped to 64x64: the full-size one-clip step took %.1f s]" % t1
+    for _ in range(max(1, args.warmup)):
         fn()
     t0 = time.time()
     for _ in range(args.steps):
@@ -171,12 +218,15 @@ def run_reference(args):
     dt = time.time() - t0
     value = frames * args.steps / dt
     cores = torch.get_num_threads()
+    sample += "; %d of the %d clips of a step, %d warm-up + %d timed steps, %.1f s" % (clips, B, max(1, args.warmup),
+                                                                                    args.steps, dt)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "device": "host CPU", "note": "reference has no CPU path; this is the "
-                   "CPU port of its training step (oracle/reference_model.py)"},
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, B, args.gpus, args.tf32,
+                                  graph=not WORKLOADS[args.workload][8] and not args.no_graph),
+        "device": "host CPU: the reference has no CPU path; this is the CPU port of its step (oracle/reference_model.py)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -346,49 +396,68 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the costliest kernel of this library inside the timed region ----
+    # ---- roofline: the kernels BASELINE.json's metric names, inside the timed region ----
+    # Headline = the costliest kernel of the workload's headline set (the separable convolutions for the TAI
+    # workloads: "sepconv % of FP32 FMA peak"; the warp / blend kernels for the SloMo baseline: "% of HBM"),
+    # timed by CUDA events the library records on its own stream around each launch.  The costliest kernel of
+    # the whole library (an epilogue kernel in the training step) is kept beside it as `library_top`.
     peaks = measured_peaks()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fma_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s, nominal at the max SM clock
+    fma_src = "%d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz, %s); not a tensor-core kernel" % (
+        sms, peaks["sm_max_mhz"], peaks["source"])
     total_kernel_ms = sum(k["ms"] for k in kernel_times) or 1.0
     kernel_times.sort(key=lambda k: -k["ms"])
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.isfile(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {})
-    roofline, per_kernel = None, []
-    for k in kernel_times:
+    traffic = load_traffic(args.workload)
+
+    def entry_of(k):
         avg_s = k["ms"] * 1e-3 / max(1, k["launches"])
-        entry = {"kernel": k["name"], "launches_per_step": k["launches"] / args.steps,
-                 "avg_us": avg_s * 1e6, "share_of_library_time": k["ms"] / total_kernel_ms,
-                 "share_of_step": k["ms"] / ms,
-                 "tflops": k["flops"] / max(1, k["launches"]) / avg_s / 1e12 if k["flops"] else 0.0,
-                 "gbs": k["bytes"] / max(1, k["launches"]) / avg_s / 1e9}
-        per_kernel.append(entry)
-    if per_kernel:
-        top = per_kernel[0]
-        compute_bound = top["tflops"] > 0
-        if compute_bound:
-            roofline = {"kernel": top["kernel"], "bound": "fp32_fma", "achieved": top["tflops"], "peak": fma_peak,
-                        "unit": "TFLOP/s", "frac": top["tflops"] / fma_peak,
-                        "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz, %s); not a tensor-core kernel"
-                                       % (sms, peaks["sm_max_mhz"], peaks["source"]),
-                        "hbm": {"achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": top["gbs"] / peaks["hbm_gbs"], "peak_source": peaks["source"]},
-                        "traffic": traffic.get(top["kernel"])}
+        return {"kernel": k["name"], "launches_per_step": k["launches"] / args.steps,
+                "avg_us": avg_s * 1e6, "share_of_library_time": k["ms"] / total_kernel_ms,
+                "share_of_step": k["ms"] / ms,
+                "tflops": k["flops"] / max(1, k["launches"]) / avg_s / 1e12 if k["flops"] else 0.0,
+                "gbs": k["bytes"] / max(1, k["launches"]) / avg_s / 1e9,
+                "algorithmic_bytes": k["bytes"] / max(1, k["launches"]),
+                "algorithmic_flop": k["flops"] / max(1, k["launches"])}
+
+    def roofline_of(e):
+        t = traffic.get(e["kernel"])
+        if e["tflops"] > 0:   # the separable convolutions: FP32 CUDA-core FMA roof (HBM figures beside it)
+            r = {"kernel": e["kernel"], "bound": "fp32_fma", "achieved": e["tflops"], "peak": fma_peak,
+                 "unit": "TFLOP/s", "frac": e["tflops"] / fma_peak, "peak_source": fma_src,
+                 "hbm_gbs": e["gbs"], "hbm_frac": e["gbs"] / peaks["hbm_gbs"]}
         else:
-            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": top["gbs"] / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                        "traffic": traffic.get(top["kernel"])}
-        roofline["avg_launch_us"] = top["avg_us"]
-        roofline["share_of_step"] = top["share_of_step"]
+            r = {"kernel": e["kernel"], "bound": "hbm", "achieved": e["gbs"], "peak": peaks["hbm_gbs"],
+                 "unit": "GB/s", "frac": e["gbs"] / peaks["hbm_gbs"], "peak_source": peaks["source"]}
+        r["traffic"] = t["dram_bytes"] if t else None
+        r["traffic_shape"] = t["shape"] if t else None
+        r["algorithmic"] = e["algorithmic_flop"] if e["tflops"] > 0 else e["algorithmic_bytes"]
+        r["avg_launch_us"] = e["avg_us"]
+        r["launches_per_step"] = e["launches_per_step"]
+        r["share_of_step"] = e["share_of_step"]
+        return r
+
+    per_kernel = [entry_of(k) for k in kernel_times]
+    roofline = None
+    if per_kernel:
+        headline = [e for e in per_kernel if e["kernel"] in HEADLINE_KERNELS[args.workload]]
+        roofline = roofline_of(headline[0] if headline else per_kernel[0])
+        # every headline kernel, flat (scalar keys survive any parser) and as objects
+        for e in headline:
+            r = roofline_of(e)
+            short = e["kernel"].replace("sepconv_", "")
+            roofline["%s_frac" % short] = r["frac"]
+            roofline["%s_avg_us" % short] = r["avg_launch_us"]
+            roofline["%s_traffic" % short] = r["traffic"]
+        roofline["headline_kernels"] = {e["kernel"]: roofline_of(e) for e in headline}
+        roofline["library_top"] = roofline_of(per_kernel[0])
         roofline["kernels"] = per_kernel
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()
-        fn, cframes, sample = cpu_reference_step_factory(args.workload)
+        clips, _ = cpu_clips_for_budget(args.workload, 12.0, 2, B)   # one warm-up + about 10 s of CPU work
+        fn, cframes, sample = cpu_reference_step_factory(args.workload, clips=clips)
         fn()                                   # warm-up (thread pools, oneDNN primitive caches)
         t0 = time.time()
         n = 0
@@ -400,15 +469,11 @@ def run_b200(args):
                         "sample": sample + "; 1 warm-up + %d timed steps, %.1f s" % (n, dt)}
 
     line = {
-        "metric": METRIC if training else "bi-TAI inpainted frames/sec (inference forward pass, %s)" % args.workload, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model_key": key, "clips_per_gpu": B, "global_clips": B * world,
-                   "frame": [c, H, W], "K": K, "T": T, "F": F_, "training": training, "ks": 51,
-                   "conv_math": "tf32" if args.tf32 else "fp32 (cudnn.allow_tf32=False)",
-                   "launch": "cuda-graph replay of the forward pass" if info["graph"] else "eager",
-                   "parallelism": "dp%d (clips sharded, NCCL all-reduce of gradients only)" % world,
-                   "l2": "per-step working set (activations, 4 x 107 MB kernel maps per middle frame) >> 126 MB L2"},
+        "config": workload_config(args.workload, B, world, args.tf32, info["graph"]),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -27,3 +27,29 @@ def assert_close(x, ref, tol=TOL, what=""):
 def to_cuda(*arrays):
     import torch
     return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+
+
+def name_seeded_state_dict(template):
+    """Deterministic weights for networks too large to commit (tests/golden/make_full_config_golden.py): every
+    tensor of `template` (a state_dict; only keys, shapes and dtypes are used) is drawn from a generator seeded
+    with crc32(key).  Convolution / linear weights: xavier-normal (gain 1, the reference's weights_init,
+    util.py:193-202); biases: uniform(-0.1, 0.1) (the reference zeroes them; non-zero biases keep an O(1) signal in
+    every branch of a randomly initialised network)."""
+    import math
+    import zlib
+
+    import torch
+    out = {}
+    for key, ref in template.items():
+        g = torch.Generator().manual_seed(zlib.crc32(key.encode()))
+        shape = tuple(ref.shape)
+        if len(shape) >= 2:
+            rf = 1
+            for s in shape[2:]:
+                rf *= s
+            std = math.sqrt(2.0 / ((shape[0] + shape[1]) * rf))
+            t = torch.randn(shape, generator=g) * std
+        else:
+            t = torch.rand(shape, generator=g) * 0.2 - 0.1
+        out[key] = t.to(ref.dtype)
+    return out

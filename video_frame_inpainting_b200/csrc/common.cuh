@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "../../include/tai_b200.h"
@@ -48,17 +50,55 @@ inline int check_launch(const char *what)
 
 inline bool fits_int31(long long n) { return n > 0 && n < (1LL << 31); }
 
+// Launch configuration is PER DEVICE (cudaFuncSetAttribute applies to the current device only) and the
+// library may be called from several host threads: small per-device tables of atomics, filled on first use
+// (the fill is idempotent, so a race only repeats it).
+constexpr int kMaxDevices = 64;
+
+inline int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 inline int sm_count()
 {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
+    static std::atomic<int> cached[kMaxDevices];
+    const int dev = current_device();
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
 }
+
+// One table per launcher (a `static KernelConfig cfg;` next to the launch): raises the dynamic shared-memory
+// limit of `kern` on the current device once and remembers how many CTAs of it fit on an SM.
+struct KernelConfig {
+    std::atomic<int> ctas[kMaxDevices];
+    // > 0: resident CTAs per SM; -1: the kernel cannot run with `smem` bytes on this device
+    template <class K>
+    int get(K kern, size_t smem, int nthreads)
+    {
+        const int dev = current_device();
+        int c = ctas[dev].load(std::memory_order_acquire);
+        if (c == 0) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                cudaGetLastError();
+                c = -1;
+            } else {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem);
+                c = occ > 0 ? occ : 1;
+            }
+            ctas[dev].store(c, std::memory_order_release);
+        }
+        return c;
+    }
+};
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

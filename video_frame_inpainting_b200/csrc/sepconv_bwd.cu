@@ -7,9 +7,12 @@
 // The reference launches three kernels that each re-walk the ks x ks window (kernel.cu:200-239).
 // Here gV and gH come out of ONE pass over the window (the same LDS of I feeds both), with the
 // lane layout of the forward kernel; gI is a separate gather kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sepconv_bwd_vh_v3.cuh"
 #include "sepconv_bwd_i_v3.cuh"
+#include "sepconv_bwd_i_v4.cuh"
 
 namespace tai {
 
@@ -411,11 +414,8 @@ static int launch_vh_tiled(const BwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, TILE_H);
     const size_t smem = (size_t)CG * (TILE_H + p.ks - 1) * PITCH * sizeof(float);
     auto kern = sepconv_bwd_vh_kernel<J, CG, WX, WY, PAD>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
-    }
+    static KernelConfig kcfg;
+    kcfg.get(kern, 160 * 1024, 32 * WX * WY);
     double fl, by;
     vh_work<PAD>(p, &fl, &by);
     {
@@ -439,16 +439,9 @@ static int launch_vh_v3(const BwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, Cfg::TILE_H);
     auto kern = sepconv_bwd_vh_v3_kernel<KS, CG, PAD>;
     const size_t smem = Cfg::smem_bytes(CG);
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
-        ctas_per_sm = occ > 0 ? occ : 1;
-    }
+    static KernelConfig kcfg;
+    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
+    if (ctas_per_sm < 0) return 1;
     long ctas = (long)p.B * p.nty * p.ntx;
     const long resident = (long)sm_count() * ctas_per_sm;
     if (ctas > resident) ctas = resident;
@@ -520,16 +513,9 @@ static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, Cfg::TILE_H);
     auto kern = sepconv_bwd_i_v3_kernel<KS>;
     const size_t smem = Cfg::smem_bytes();
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
-        ctas_per_sm = occ > 0 ? occ : 1;
-    }
+    static KernelConfig kcfg;
+    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
+    if (ctas_per_sm < 0) return 1;
     const size_t gi_bytes = sizeof(float) * (size_t)p.B * p.C * (p.Ho + KS - 1) * (p.Wo + KS - 1);
     cudaError_t e = cudaMemsetAsync(p.gin, 0, gi_bytes, st);  // the kernel accumulates with red.global
     if (e != cudaSuccess) {
@@ -548,16 +534,59 @@ static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
     return check_launch("sepconv_bwd_i_v3_kernel");
 }
 
+// Same data movement, cheaper reduction of the warp rows (sepconv_bwd_i_v4.cuh).
+template <int KS, bool FOLD>
+static int launch_gi_v4(const BwdParams &p0, cudaStream_t st)
+{
+    using Cfg = GiV4Cfg<KS>;
+    BwdParams p = p0;
+    GiV4Maps maps;
+    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+        !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
+        return 1;
+    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
+    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
+    auto kern = sepconv_bwd_i_v4_kernel<KS, FOLD>;
+    const size_t smem = Cfg::smem_bytes();
+    static KernelConfig kcfg;
+    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
+    if (ctas_per_sm < 0) return 1;
+    const size_t gi_bytes = sizeof(float) * (size_t)p.B * p.C * (p.Ho + KS - 1) * (p.Wo + KS - 1);
+    cudaError_t e = cudaMemsetAsync(p.gin, 0, gi_bytes, st);  // the kernel accumulates with red.global
+    if (e != cudaSuccess) {
+        set_error("sepconv_bwd_i_v4: memset: %s", cudaGetErrorString(e));
+        return TAI_ERR_CUDA;
+    }
+    long ctas = (long)p.B * p.nty * p.ntx;
+    const long resident = (long)sm_count() * ctas_per_sm;
+    if (ctas > resident) ctas = resident;
+    double fl, by;
+    gi_work(p, &fl, &by);
+    {
+        TimingScope ts("sepconv_bwd_i", st, fl, by);
+        kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
+    }
+    return check_launch("sepconv_bwd_i_v4_kernel");
+}
+
+template <int KS>
+static int launch_gi_tma(const BwdParams &p, cudaStream_t st)
+{
+    static const bool use_v3 = getenv("TAI_GI_V3") != nullptr;  // A/B switch while v4 is being measured
+    if (use_v3) return launch_gi_v3<KS>(p, st);
+    return p.C == 1 ? launch_gi_v4<KS, true>(p, st) : launch_gi_v4<KS, false>(p, st);
+}
+
 static int launch_gi(const BwdParams &p, cudaStream_t st)
 {
     const int Hi = p.Ho + p.ks - 1, Wi = p.Wo + p.ks - 1;
     {
         int rc = 1;
         switch (p.ks) {
-            case 51: rc = launch_gi_v3<51>(p, st); break;
-            case 37: rc = launch_gi_v3<37>(p, st); break;
-            case 25: rc = launch_gi_v3<25>(p, st); break;
-            case 13: rc = launch_gi_v3<13>(p, st); break;
+            case 51: rc = launch_gi_tma<51>(p, st); break;
+            case 37: rc = launch_gi_tma<37>(p, st); break;
+            case 25: rc = launch_gi_tma<25>(p, st); break;
+            case 13: rc = launch_gi_tma<13>(p, st); break;
             default: break;
         }
         if (rc <= 0) return rc;

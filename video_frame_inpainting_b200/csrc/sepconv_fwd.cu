@@ -262,11 +262,8 @@ static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, TILE_H);
     const size_t smem = (size_t)CG * (TILE_H + p.ks - 1) * PITCH * sizeof(float);
     auto kern = sepconv_fwd_kernel<J, CG, WX, WY, PAD, DUAL>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
-    }
+    static KernelConfig kcfg;
+    kcfg.get(kern, 160 * 1024, 32 * WX * WY);
     const long blocks = (long)p.B * p.nty * p.ntx;
     double fl, by;
     fwd_work<PAD, DUAL>(p, &fl, &by);
@@ -298,16 +295,9 @@ static int launch_fwd_v3(const FwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, Cfg::TILE_H);
     auto kern = sepconv_fwd_v3_kernel<KS, CG, PAD, DUAL>;
     const size_t smem = Cfg::smem_bytes(CG);
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
-        ctas_per_sm = occ > 0 ? occ : 1;
-    }
+    static KernelConfig kcfg;
+    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
+    if (ctas_per_sm < 0) return 1;
     long ctas = (long)p.B * p.nty * p.ntx;
     const long resident = (long)sm_count() * ctas_per_sm;
     if (ctas > resident) ctas = resident;
@@ -348,16 +338,9 @@ static int launch_fwd_v5(const FwdParams &p0, cudaStream_t st)
     p.nty = ceil_div(p.Ho, Cfg::TILE_H);
     auto kern = sepconv_fwd_v5_kernel<KS, CG, PAD, DUAL>;
     const size_t smem = Cfg::smem_bytes(CG);
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, smem);
-        ctas_per_sm = occ > 0 ? occ : 1;
-    }
+    static KernelConfig kcfg;
+    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
+    if (ctas_per_sm < 0) return 1;
     // one contiguous tile range per CTA, balanced per SM first (blockIdx % nsm shares an SM in practice)
     const long ntiles = (long)p.B * p.nty * p.ntx;
     const int nsm = (int)(ntiles < sm_count() ? ntiles : sm_count());

@@ -19,6 +19,7 @@ import os
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from .. import ops
 from ..discriminators.SNDiscriminator import SNDiscriminator
@@ -125,7 +126,14 @@ class BaseVideoFillInEnvironment(object):
         save_path = os.path.join(self.save_dir, snapshot_file_name)
         if not os.path.isfile(save_path):
             raise RuntimeError('Failed to find snapshot at path %s' % save_path)
-        snapshot = torch.load(save_path, map_location='cuda')
+        # The reference writes its checkpoints with torch 0.3.1 / Python 2 and keeps numpy scalars in them
+        # (train.py:163 passes np.sum(np.mean(...)) as sum_avg_psnr_err): the weights_only unpickler of
+        # torch >= 2.6 rejects those, and py2 pickles need latin1.  Checkpoints are trusted input here, as
+        # they are for the reference's torch.load (environments.py:104).
+        try:
+            snapshot = torch.load(save_path, map_location='cuda', weights_only=False)
+        except UnicodeDecodeError:
+            snapshot = torch.load(save_path, map_location='cuda', weights_only=False, encoding='latin1')
         self.generator.load_state_dict(snapshot['generator'])
         return snapshot
 
@@ -147,8 +155,15 @@ class BaseTrainingEnvironment(BaseVideoFillInEnvironment):
 
     def sample_KTF(self, allow_random_sampling):
         if allow_random_sampling:
-            return (np.random.randint(1, self.max_K + 1), np.random.randint(1, self.max_T + 1),
-                    np.random.randint(1, self.max_F + 1))
+            ktf = [np.random.randint(1, self.max_K + 1), np.random.randint(1, self.max_T + 1),
+                   np.random.randint(1, self.max_F + 1)]
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # every rank must run the same graph (K switches the batched-history path, T the number of
+                # sepconv launches): rank 0's draw wins (the reference is single-process, environments.py:417-427)
+                t = torch.tensor(ktf, device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
+                dist.broadcast(t, 0)
+                ktf = [int(v) for v in t.tolist()]
+            return tuple(ktf)
         return self.max_K, self.max_T, self.max_F
 
     def set_train_inputs(self, preceding_frames, following_frames, gt_middle_frames):
@@ -161,9 +176,9 @@ class BaseTrainingEnvironment(BaseVideoFillInEnvironment):
 
     def get_current_state_dict(self, total_updates, sum_avg_psnr_err, sum_avg_ssim_err):
         return {
-            'updates': total_updates,
-            'sum_avg_psnr_err': sum_avg_psnr_err,
-            'sum_avg_ssim_err': sum_avg_ssim_err,
+            'updates': int(total_updates),
+            'sum_avg_psnr_err': float(sum_avg_psnr_err),   # numpy scalars in the reference's train loop (train.py:163)
+            'sum_avg_ssim_err': float(sum_avg_ssim_err),
             'generator': self.generator.state_dict(),
             'optimizer_G': self.optimizer_G.state_dict(),
         }
@@ -177,9 +192,17 @@ class BaseTrainingEnvironment(BaseVideoFillInEnvironment):
         return snapshot
 
     def save(self, snapshot_file_name, total_updates, sum_avg_psnr_err, sum_avg_ssim_err):
-        os.makedirs(self.save_dir, exist_ok=True)
-        torch.save(self.get_current_state_dict(total_updates, sum_avg_psnr_err, sum_avg_ssim_err),
-                   os.path.join(self.save_dir, snapshot_file_name))
+        """environments.py:186-194.  Replicas are bit-identical, so rank 0 alone writes (to a temporary file
+        moved into place: a reader never sees a torn checkpoint) and the other ranks wait for it."""
+        multi = dist.is_available() and dist.is_initialized()
+        if not multi or dist.get_rank() == 0:
+            os.makedirs(self.save_dir, exist_ok=True)
+            path = os.path.join(self.save_dir, snapshot_file_name)
+            tmp = path + '.tmp.%d' % os.getpid()
+            torch.save(self.get_current_state_dict(total_updates, sum_avg_psnr_err, sum_avg_ssim_err), tmp)
+            os.replace(tmp, path)
+        if multi:
+            dist.barrier()
 
     def optimize_parameters(self):
         """One generator update (environments.py:222-228)."""
@@ -349,7 +372,13 @@ class SloMoTrainingEnvironment(BaseTrainingEnvironment):
         vgg16 = torchvision.models.vgg16(weights=None)
         if vgg16_state_dict is not None:
             vgg16.load_state_dict(vgg16_state_dict)
-        self.vgg16_conv = torch.nn.Sequential(*list(vgg16.features.children())[:22]).cuda()   # up to conv4_3 + ReLU
+        elif lambda_p != 0:
+            import warnings
+            warnings.warn("SloMoTrainingEnvironment: no vgg16_state_dict given -- the perceptual loss (lambda_p=%g) "
+                          "is computed on RANDOMLY INITIALISED VGG-16 features; the reference uses the ImageNet "
+                          "weights (environments.py:541).  Pass torchvision's vgg16 state_dict for real training."
+                          % lambda_p)
+        self.vgg16_conv = torch.nn.Sequential(*list(vgg16.features.children())[:22]).cuda()   # features[:22]: up to conv4_3, no ReLU (as the reference)
         for param in self.vgg16_conv.parameters():
             param.requires_grad = False
         self.warper = FlowWarper()

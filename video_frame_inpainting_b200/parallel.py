@@ -84,6 +84,7 @@ class FlatGradAllReducer(object):
                 self._bucket_of[p] = bi
             self._slices.append((offset, hi))
         self._pending = [0] * len(self.buckets)
+        self._next = 0
         self._handles = []
         self._armed = False
         for p in self.params:
@@ -104,16 +105,24 @@ class FlatGradAllReducer(object):
         """Call right before backward(): buckets are reduced as soon as their last gradient lands."""
         self._pending = [len(b) for b in self.buckets]
         self._handles = []
+        self._next = 0       # buckets are launched strictly in index order on every rank
         self._armed = True
+
+    def _launch_ready(self, force=False):
+        """Launch bucket i only after buckets 0..i-1: every rank issues the same sequence of collectives even when
+        its hooks complete in a different order (a graph that differs between ranks, unused parameters) --
+        differently sized all-reduces paired across ranks would hang or sum the wrong slices."""
+        while self._next < len(self.buckets) and (force or self._pending[self._next] == 0):
+            lo, hi = self._slices[self._next]
+            self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._next += 1
 
     def _hook(self, p):
         if not self._armed:
             return
-        bi = self._bucket_of[p]
-        self._pending[bi] -= 1
-        if self._pending[bi] == 0 and self.active:
-            lo, hi = self._slices[bi]
-            self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self._pending[self._bucket_of[p]] -= 1
+        if self.active:
+            self._launch_ready()
 
     def finish(self):
         """Call after backward(): reduce buckets whose hooks did not all fire (unused parameters), wait,
@@ -123,10 +132,7 @@ class FlatGradAllReducer(object):
         self._armed = False
         if not self.active:
             return
-        for bi, left in enumerate(self._pending):
-            if left > 0:
-                lo, hi = self._slices[bi]
-                self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self._launch_ready(force=True)   # buckets whose hooks did not all fire, still in index order
         for h in self._handles:
             h.wait()
         self._handles = []
