@@ -35,6 +35,8 @@ UNIT = "frames/s"
 
 
 def metric_name(workload):
+    if workload == "slomo_train_b4":
+        return "Super SloMo interpolated frames/sec (training step: fwd + bwd + Adam)"
     if WORKLOADS[workload][8]:
         return METRIC
     return "bi-TAI inpainted frames/sec (inference forward pass, %s)" % workload
@@ -45,6 +47,11 @@ WORKLOADS = {
     "kth_infer_b1": ("TAI_gray", 1, 128, 128, 5, 5, 5, 1, False),
     "ucf_infer_b8": ("TAI_color", 3, 240, 320, 5, 3, 5, 8, False),
     "slomo_infer_b8": ("SloMoFillInModel_color", 3, 256, 320, 2, 3, 2, 8, False),
+    # the reference's own UCF test arguments (exp_args/default_args/UCF-101/test_3.txt:1-7): K = F = 4, batch 16
+    "ucf_infer_ref443_b16": ("TAI_color", 3, 240, 320, 4, 3, 4, 16, False),
+    # Super SloMo training step at the reference's training size and default batch (SuperSloMo_train.txt:3,
+    # options.py:22,164-175); the perceptual loss runs on randomly initialised VGG-16 features (no network here)
+    "slomo_train_b4": ("SloMoFillInModel_color", 3, 160, 192, 4, 3, 4, 4, True),
 }
 TRAIN_HP = dict(alpha=1.0, beta=0.02, lr=1e-4, beta1=0.5, df_dim=64, Ip=3, disc_window_size=3)  # options.py:72-99
 
@@ -64,9 +71,10 @@ def parse_args():
 
 
 SEPCONV_KERNELS = ("sepconv_fused_fwd", "sepconv_fwd", "sepconv_bwd_vh", "sepconv_bwd_i")
-WARP_KERNELS = ("slomo_combine_warp", "slomo_refine_blend", "warp_fwd", "warp_bwd")
+WARP_KERNELS = ("slomo_interp_input", "slomo_refine_blend_t", "slomo_interp_input_bwd", "slomo_refine_blend_t_bwd",
+                "slomo_combine_warp", "slomo_refine_blend", "warp_fwd", "warp_bwd")
 HEADLINE_KERNELS = {"kth_train_b32": SEPCONV_KERNELS, "kth_infer_b1": SEPCONV_KERNELS, "ucf_infer_b8": SEPCONV_KERNELS,
-                    "slomo_infer_b8": WARP_KERNELS}
+                    "ucf_infer_ref443_b16": SEPCONV_KERNELS, "slomo_infer_b8": WARP_KERNELS, "slomo_train_b4": WARP_KERNELS}
 
 
 def load_traffic(workload):
@@ -266,7 +274,15 @@ def build_workload(workload, batch=0, tf32=False, rank=0, local_rank=0, graph=Tr
                 m.batch_history = os.environ["TAI_BATCH_HISTORY"] == "1"
     if os.environ.get("TAI_BATCH_TIME") in ("0", "1") and hasattr(model, "batch_time"):
         model.batch_time = os.environ["TAI_BATCH_TIME"] == "1"
-    if training:
+    if training and key.startswith("SloMo"):
+        import warnings
+        from video_frame_inpainting_b200.environments.environments import SloMoTrainingEnvironment
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")   # random VGG-16 features: stated in the workload's description
+            env = SloMoTrainingEnvironment(model, "/tmp/tai_b200_ckpt", "bench", 1e-4, 0.5, K, T, F_, (0, 0), 0.8, 0.005,
+                                           0.4, 1, 40000, 0.1)
+        env.train()
+    elif training:
         env = TAITrainingEnvironment(model, "/tmp/tai_b200_ckpt", "bench", (H, W), c, TRAIN_HP["alpha"],
                                      TRAIN_HP["beta"], TRAIN_HP["lr"], TRAIN_HP["beta1"], TRAIN_HP["df_dim"],
                                      TRAIN_HP["Ip"], TRAIN_HP["disc_window_size"], K, T, F_, (0, 0))
@@ -454,7 +470,7 @@ def run_b200(args):
         roofline["kernels"] = per_kernel
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not (training and key.startswith("SloMo")):
         torch.cuda.empty_cache()
         clips, _ = cpu_clips_for_budget(args.workload, 12.0, 2, B)   # one warm-up + about 10 s of CPU work
         fn, cframes, sample = cpu_reference_step_factory(args.workload, clips=clips)

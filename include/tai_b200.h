@@ -39,6 +39,11 @@ const char *tai_b200_last_error(void);
  * used by bench.py for its "gpu_launches" claim). */
 long long tai_b200_launch_count(void);
 
+/* Which kernel family the last separable-convolution launch of this thread took: "fwd:v3" / "fwd:v5" (persistent,
+ * TMA-fed), "fwd:tiled" (LDG-fed, any ks <= 64: shapes TMA cannot describe, W % 4 != 0 or a misaligned base),
+ * "fwd:simple" (shape-agnostic); "bwd_vh:*", "bwd_i:*" likewise.  Static string; for the op sweep's report. */
+const char *tai_b200_last_path(void);
+
 /* Measurement support for bench.py: when enabled every kernel launch of this library is bracketed by
  * CUDA events on its own stream; the report is a JSON array of
  * {"name","launches","ms","flops","bytes"} (ms = summed event time, flops/bytes = the ALGORITHMIC work
@@ -152,6 +157,38 @@ int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
                                     const float *d_t0, const float *d_t1, const float *v_t0,
                                     double t, float *out, int B, int C, int H, int W, void *stream);
 
+/* The same two stages for ALL T middle frames of a batch in one launch each, with their adjoints
+ * (slomo.py:307-340: the per-t loop of SloMo.forward; the time steps are independent).  t = (t_+1)/(T+1) in
+ * double as in the reference (slomo.py:2,312); T <= 16.  Sample order of the T*B batch: n = t_*B + b.
+ *
+ * slomo_interp_input_*: slomo.py:312-318.  interp_input [T*B, 4C+4, H, W] is the refinement network's input
+ * cat(I0, g(I0,F_t0), F_t0, F_t1, g(I1,F_t1), I1) (slomo.py:318), written in place; f_t{0,1}_collector
+ * [B,T,2,H,W] are the model's F_t_*_collector outputs in the reference's REVERSED time order
+ * (slot T-1-t_, slomo.py:332-340).  Backward: g_f01 / g_f10 [B,2,H,W] from the gradients of all three outputs
+ * (collector gradients may be NULL); gather-only, no atomics, deterministic.  Gradients w.r.t. i0 / i1 are not
+ * produced (network inputs): use flow_warp_backward_b200 for those. */
+int slomo_interp_input_forward_b200(const float *i0, const float *i1, const float *f01, const float *f10,
+                                    float *interp_input, float *f_t0_collector, float *f_t1_collector,
+                                    int B, int T, int C, int H, int W, void *stream);
+int slomo_interp_input_backward_b200(const float *i0, const float *i1, const float *f01, const float *f10,
+                                     const float *g_interp_input, const float *g_f_t0_collector,
+                                     const float *g_f_t1_collector, float *g_f01, float *g_f10,
+                                     int B, int T, int C, int H, int W, void *stream);
+/* slomo_refine_blend_batched_*: slomo.py:320-328 for every (t_, b).  d_t0, d_t1 [T*B,2,H,W], v_t0 [T*B,1,H,W]
+ * (the refinement network's outputs, sample order n = t_*B + b); the flows are read from the collectors; pred
+ * [B,T,C,H,W] in the reference's reversed time order.  Backward: gradients w.r.t. the collectors, d_t0, d_t1
+ * (torch.clamp's mask: gradient passes on [-1, 1] inclusive) and v_t0; gather-only. */
+int slomo_refine_blend_batched_forward_b200(const float *i0, const float *i1, const float *f_t0_collector,
+                                            const float *f_t1_collector, const float *d_t0, const float *d_t1,
+                                            const float *v_t0, float *pred,
+                                            int B, int T, int C, int H, int W, void *stream);
+int slomo_refine_blend_batched_backward_b200(const float *i0, const float *i1, const float *f_t0_collector,
+                                             const float *f_t1_collector, const float *d_t0, const float *d_t1,
+                                             const float *v_t0, const float *g_pred,
+                                             float *g_f_t0_collector, float *g_f_t1_collector, float *g_d_t0,
+                                             float *g_d_t1, float *g_v_t0,
+                                             int B, int T, int C, int H, int W, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Decoder resampling.  N = B*C planes of H x W; results are 2H x 2W.
  *
@@ -219,6 +256,23 @@ int bias_act_backward_b200(const float *grad_out, const float *out, float *grad_
  * replaces `_l2normalize` of src/discriminators/SNDiscriminator.py:5-7 (pow, sum, pow, add, div -- five launches,
  * called twice per power iteration of every spectral-norm layer: 1170 times per KTH training step). */
 int l2_normalize_b200(const float *v, float *out, int n, float eps, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Motion-stream prologue.  Replaces the elementwise chains of
+ * src/models/tai/tai.py:67-74 (inverse_transform -> bgr2gray_batched -> frame differences, and the same on the
+ * time-reversed following frames), src/models/mcnet/mcnet.py:439-447 (the next motion input inside the
+ * prediction loop) and src/util/util.py:22-41.  FP32 with one rounding per reference operation: bit-identical.
+ *
+ * gray_difference_frames: frames [B,K,C,H,W] in [-1,1] -> out [B,K-1,1,H,W];
+ *   out[b,k] = gray01(frame i(k+1)) - gray01(frame i(k)), i(k) = k, or K-1-k when `reverse` (no flip copy).
+ * gray_difference_pair:   a, b [N,C,H,W] -> out [N,1,H,W] = gray01(a) - gray01(b); backward writes
+ *   g_a = 0.5 w_c g and / or g_b = -0.5 w_c g (either may be NULL).  C must be 1 or 3 (BGR). */
+int gray_difference_frames_b200(const float *frames, float *out, int B, int K, int C, int H, int W, int reverse,
+                                void *stream);
+int gray_difference_pair_forward_b200(const float *a, const float *b, float *out, long long N, int C, int H, int W,
+                                      void *stream);
+int gray_difference_pair_backward_b200(const float *grad_out, float *g_a, float *g_b, long long N, int C, int H, int W,
+                                       void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Output side: frames in [-1, 1] -> 8-bit interleaved images.

@@ -381,6 +381,83 @@ def slomo_refine_blend(i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, t):
     return ((1 - t) * v0 * g0 + t * v1 * g1) / norm
 
 
+def slomo_interp_input(i0, i1, f01, f10, T):
+    """The per-t loop of slomo.py:307-318 for all T middle frames: returns
+    X [T*B, 4C+4, H, W] = cat(I0, g(I0,F_t0), F_t0, F_t1, g(I1,F_t1), I1) per t (sample n = t_*B + b), and the
+    collectors F_t_0 / F_t_1 [B,T,2,H,W] in the reference's REVERSED time order (new frames are prepended,
+    slomo.py:332-340: slot T-1-t_)."""
+    i0, i1 = np.asarray(i0, np.float64), np.asarray(i1, np.float64)
+    B, C, H, W = i0.shape
+    X = np.zeros((T * B, 4 * C + 4, H, W))
+    c0, c1 = np.zeros((B, T, 2, H, W)), np.zeros((B, T, 2, H, W))
+    for t_ in range(T):
+        t = (t_ + 1) / (T + 1)
+        ft0, ft1 = slomo_flow_combine(f01, f10, t)
+        X[t_ * B:(t_ + 1) * B] = np.concatenate((i0, flow_warp(i0, ft0), ft0, ft1, flow_warp(i1, ft1), i1), 1)
+        c0[:, T - 1 - t_], c1[:, T - 1 - t_] = ft0, ft1
+    return X, c0, c1
+
+
+def slomo_interp_input_backward(i0, i1, f01, f10, T, gX, gc0=None, gc1=None):
+    """Adjoint of slomo_interp_input w.r.t. (F_0_1, F_1_0); float64."""
+    i0, i1 = np.asarray(i0, np.float64), np.asarray(i1, np.float64)
+    f01, f10, gX = np.asarray(f01, np.float64), np.asarray(f10, np.float64), np.asarray(gX, np.float64)
+    B, C, H, W = i0.shape
+    g01, g10 = np.zeros_like(f01), np.zeros_like(f10)
+    for t_ in range(T):
+        t = (t_ + 1) / (T + 1)
+        ft0, ft1 = slomo_flow_combine(f01, f10, t)
+        g = gX[t_ * B:(t_ + 1) * B]
+        g0 = flow_warp_backward(i0, ft0, g[:, C:2 * C])[1] + g[:, 2 * C:2 * C + 2]
+        g1 = flow_warp_backward(i1, ft1, g[:, 2 * C + 4:3 * C + 4])[1] + g[:, 2 * C + 2:2 * C + 4]
+        if gc0 is not None:
+            g0 = g0 + np.asarray(gc0, np.float64)[:, T - 1 - t_]
+        if gc1 is not None:
+            g1 = g1 + np.asarray(gc1, np.float64)[:, T - 1 - t_]
+        g01 += -(1 - t) * t * g0 + (1 - t) * (1 - t) * g1
+        g10 += t ** 2 * g0 - t * (1 - t) * g1
+    return g01, g10
+
+
+def slomo_refine_blend_batched(i0, i1, c0, c1, d0, d1, v0, T):
+    """slomo.py:320-340 for all T middle frames: pred [B,T,C,H,W] in reversed time order; the refinement outputs
+    d0, d1 [T*B,2,H,W], v0 [T*B,1,H,W] in sample order n = t_*B + b, the flows from the collectors."""
+    B, C, H, W = np.asarray(i0).shape
+    pred = np.zeros((B, T, C, H, W))
+    for t_ in range(T):
+        t = (t_ + 1) / (T + 1)
+        sl = slice(t_ * B, (t_ + 1) * B)
+        pred[:, T - 1 - t_] = slomo_refine_blend(i0, i1, np.asarray(c0)[:, T - 1 - t_], np.asarray(c1)[:, T - 1 - t_],
+                                                 np.asarray(d0)[sl], np.asarray(d1)[sl], np.asarray(v0)[sl], t)
+    return pred
+
+
+def slomo_refine_blend_batched_backward(i0, i1, c0, c1, d0, d1, v0, T, gpred):
+    """Adjoint of slomo_refine_blend_batched w.r.t. (collectors, d0, d1, v0); float64.  torch.clamp passes the
+    gradient on [-1, 1] inclusive."""
+    i0, i1 = np.asarray(i0, np.float64), np.asarray(i1, np.float64)
+    c0, c1, d0, d1, v0, gpred = (np.asarray(a, np.float64) for a in (c0, c1, d0, d1, v0, gpred))
+    B, C, H, W = i0.shape
+    gc0, gc1, gd0, gd1, gv0 = (np.zeros_like(a) for a in (c0, c1, d0, d1, v0))
+    for t_ in range(T):
+        t = (t_ + 1) / (T + 1)
+        sl, slot = slice(t_ * B, (t_ + 1) * B), T - 1 - t_
+        s0, s1 = d0[sl] + c0[:, slot], d1[sl] + c1[:, slot]
+        r0, r1 = np.clip(s0, -1, 1), np.clip(s1, -1, 1)
+        a0, a1 = flow_warp(i0, r0), flow_warp(i1, r1)
+        V = v0[sl]
+        k0, k1 = (1 - t) * V, t * (1 - V)
+        n = k0 + k1
+        g = gpred[:, slot]
+        out = (k0 * a0 + k1 * a1) / n
+        gv0[sl] = (g * (((1 - t) * a0 - t * a1) - out * ((1 - t) - t)) / n).sum(1, keepdims=True)
+        gr0 = flow_warp_backward(i0, r0, g * k0 / n)[1] * ((s0 >= -1) & (s0 <= 1))
+        gr1 = flow_warp_backward(i1, r1, g * k1 / n)[1] * ((s1 >= -1) & (s1 <= 1))
+        gd0[sl], gd1[sl] = gr0, gr1
+        gc0[:, slot], gc1[:, slot] = gr0, gr1
+    return gc0, gc1, gd0, gd1, gv0
+
+
 # --------------------------------------------------------------------------------------------
 # Small glue on the call path (util.py:22-41; mcnet.py:240-256)
 # --------------------------------------------------------------------------------------------

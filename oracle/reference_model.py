@@ -137,6 +137,7 @@ def to_cpu_reference(model):
             m.__class__ = CpuFlowWarper
         elif type(m) is SloMo:
             m.__class__ = CpuSloMo
+            m.batch_time = False         # the reference's per-t loop (slomo.py:307-340)
         elif type(m) is DecCnn:
             m.__class__ = CpuDecCnn
         elif type(m) is BilinearUp2:

@@ -45,10 +45,21 @@ def test_flow_warp_forward(cuda, B, C, H, W):
     assert_close(out, O.flow_warp(img, uv, coords="f32"), tol=1e-5, what="warp (f32-coordinate twin)")
     # float64 coordinates can fall on the other side of an integer; bilinear is continuous there
     assert_close(out, O.flow_warp(img, uv), tol=2e-3, what="warp (float64 coordinates)")
-    # integer table: warping a coordinate image with zero fractional flow recovers floor() exactly
+    # Integer table, bit-exact: the bilinear value is continuous across an integer boundary, so a floor() that is off
+    # by one is invisible in `out`.  The flow gradient is not: with img = x^2 the x-derivative of the interpolant is
+    # (x0+1)^2 - x0^2 = 2*x0 + 1 wherever the four taps are inside, so floor(ix) is recovered exactly from
+    # flow_warp_backward and compared with the oracle's FP32 table (same for y).
     ix, iy, x0, y0 = O.flow_warp_coords_f32(uv)
-    frac0 = (ix == np.floor(ix)) & (iy == np.floor(iy))
-    assert frac0.sum() >= 0  # (table itself is exercised through the f32 twin above)
+    inside = (x0 >= 0) & (x0 + 1 < W) & (y0 >= 0) & (y0 + 1 < H)
+    assert inside.mean() > 0.5
+    ones = torch.ones(B, 1, H, W, device=ti.device)
+    sq_x = torch.arange(W, device=ti.device, dtype=torch.float32).pow(2).view(1, 1, 1, W).expand(B, 1, H, W).contiguous()
+    sq_y = torch.arange(H, device=ti.device, dtype=torch.float32).pow(2).view(1, 1, H, 1).expand(B, 1, H, W).contiguous()
+    gx = ops.flow_warp_backward(sq_x, tu, ones, need_img=False)[1][:, 0].cpu().numpy().astype(np.float64)
+    gy = ops.flow_warp_backward(sq_y, tu, ones, need_img=False)[1][:, 1].cpu().numpy().astype(np.float64)
+    rec_x0 = np.rint((gx * W / (W - 1) - 1) / 2).astype(np.int32)
+    rec_y0 = np.rint((gy * H / (H - 1) - 1) / 2).astype(np.int32)
+    assert np.array_equal(rec_x0[inside], x0[inside]) and np.array_equal(rec_y0[inside], y0[inside])
 
 
 def test_flow_warp_integer_corners_bit_exact(cuda):
@@ -119,6 +130,119 @@ def test_slomo_fused_stages(cuda, B, C, H, W, T):
         out = ops.slomo_refine_blend(t_i0, t_i1, ft0, ft1, t_d0, t_d1, t_v0, t).cpu().numpy()
         ref = O.slomo_refine_blend(i0, i1, ft0.cpu().numpy(), ft1.cpu().numpy(), d0, d1, v0, t)
         assert_close(out, ref, tol=2e-3, what="refine+blend")
+
+
+@pytest.mark.parametrize("B,C,H,W,T", [(1, 3, 32, 64, 3), (2, 1, 16, 24, 5), (2, 2, 12, 20, 1)])
+def test_slomo_time_batched_stages_forward_and_backward(cuda, B, C, H, W, T):
+    """slomo.py:307-340 as two launches over all T middle frames (slomo_interp_input_*, slomo_refine_blend_batched_*):
+    values against the float64 oracle, BIT-EXACT against the per-t kernels (same arithmetic, other launch shape),
+    gradients against the oracle's adjoints."""
+    import torch
+    from video_frame_inpainting_b200 import ops
+    rng = np.random.default_rng(31)
+    # smooth frames: the flow gradient of a warp is a finite difference of the image
+    def smooth(n, c):
+        low = torch.from_numpy(rng.uniform(-1, 1, (n, c, 4, 6)).astype(np.float32))
+        return torch.nn.functional.interpolate(low, size=(H, W), mode='bilinear', align_corners=True).numpy()
+    i0, i1 = smooth(B, C), smooth(B, C)
+    f01 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    f10 = np.tanh(rng.normal(0, 1, (B, 2, H, W))).astype(np.float32)
+    d0 = np.tanh(rng.normal(0, 1, (T * B, 2, H, W))).astype(np.float32)     # some sums leave [-1, 1]: clamp mask
+    d1 = np.tanh(rng.normal(0, 1, (T * B, 2, H, W))).astype(np.float32)
+    v0 = rng.uniform(0.05, 0.95, (T * B, 1, H, W)).astype(np.float32)
+    t_i0, t_i1, t_f01, t_f10, t_d0, t_d1, t_v0 = to_cuda(i0, i1, f01, f10, d0, d1, v0)
+    for t in (t_f01, t_f10, t_d0, t_d1, t_v0):
+        t.requires_grad_(True)
+    X, c0, c1 = ops.SlomoInterpInputFunction.apply(t_i0, t_i1, t_f01, t_f10, T)
+    pred = ops.SlomoRefineBlendFunction.apply(t_i0, t_i1, c0, c1, t_d0, t_d1, t_v0, T)
+    rX, rc0, rc1 = O.slomo_interp_input(i0, i1, f01, f10, T)
+    assert_close(c0.detach().cpu().numpy(), rc0, what="F_t_0 collector")
+    assert_close(c1.detach().cpu().numpy(), rc1, what="F_t_1 collector")
+    assert_close(X.detach().cpu().numpy(), rX, tol=2e-3, what="interp_input")
+    c0n, c1n = c0.detach().cpu().numpy(), c1.detach().cpu().numpy()
+    assert_close(pred.detach().cpu().numpy(), O.slomo_refine_blend_batched(i0, i1, c0n, c1n, d0, d1, v0, T), tol=2e-3,
+                 what="pred")
+    # the per-t kernels compute the same values bit for bit
+    with torch.no_grad():
+        for t_ in range(T):
+            t = (t_ + 1) / (T + 1)
+            ft0, ft1, g0, g1 = ops.slomo_flow_combine_warp(t_i0, t_i1, t_f01, t_f10, t)
+            Xt = X[t_ * B:(t_ + 1) * B]
+            assert torch.equal(Xt, torch.cat((t_i0, g0, ft0, ft1, g1, t_i1), 1))
+            assert torch.equal(c0[:, T - 1 - t_], ft0) and torch.equal(c1[:, T - 1 - t_], ft1)
+            out = ops.slomo_refine_blend(t_i0, t_i1, ft0, ft1, t_d0[t_ * B:(t_ + 1) * B].contiguous(),
+                                         t_d1[t_ * B:(t_ + 1) * B].contiguous(), t_v0[t_ * B:(t_ + 1) * B].contiguous(), t)
+            assert torch.equal(pred[:, T - 1 - t_], out)
+    # adjoints
+    gX = rng.normal(0, 1, X.shape).astype(np.float32)
+    gc0 = rng.normal(0, 1, c0.shape).astype(np.float32)
+    gc1 = rng.normal(0, 1, c1.shape).astype(np.float32)
+    gp = rng.normal(0, 1, pred.shape).astype(np.float32)
+    t_gX, t_gc0, t_gc1, t_gp = to_cuda(gX, gc0, gc1, gp)
+    ((X * t_gX).sum() + (c0 * t_gc0).sum() + (c1 * t_gc1).sum() + (pred * t_gp).sum()).backward()
+    r_gc0, r_gc1, r_gd0, r_gd1, r_gv0 = O.slomo_refine_blend_batched_backward(i0, i1, c0n, c1n, d0, d1, v0, T, gp)
+    assert_close(t_d0.grad.cpu().numpy(), r_gd0, tol=2e-3, what="g dF_t_0")
+    assert_close(t_d1.grad.cpu().numpy(), r_gd1, tol=2e-3, what="g dF_t_1")
+    assert_close(t_v0.grad.cpu().numpy(), r_gv0, tol=2e-3, what="g V_t_0")
+    r_g01, r_g10 = O.slomo_interp_input_backward(i0, i1, f01, f10, T, gX, gc0 + r_gc0, gc1 + r_gc1)
+    assert_close(t_f01.grad.cpu().numpy(), r_g01, tol=2e-3, what="g F_0_1")
+    assert_close(t_f10.grad.cpu().numpy(), r_g10, tol=2e-3, what="g F_1_0")
+
+
+def test_slomo_batched_time_equals_per_t_loop(cuda):
+    """SloMo.forward with batch_time (one pass over T*B samples) against the reference's per-t loop structure on
+    the same weights: same kernels' arithmetic per sample, the convolutions see another batch size."""
+    import torch
+    from video_frame_inpainting_b200.models.slomo.slomo import SloMoFillInModel
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(5)
+    model = SloMoFillInModel(gf_dim=4, c_input_dim=3).cuda()
+    pre, fol = torch.rand(2, 2, 3, 32, 64, device='cuda') * 2 - 1, torch.rand(2, 2, 3, 32, 64, device='cuda') * 2 - 1
+    outs = {}
+    for flag in (True, False):
+        model.generator.batch_time = flag
+        model.zero_grad()
+        out = model(3, pre, fol)
+        out['pred'].pow(2).mean().backward()
+        outs[flag] = ({k: v.detach().clone() for k, v in out.items()},
+                      model.generator.compute_enc.enc1[0].weight.grad.clone())
+    for k in outs[True][0]:
+        assert O.rel_err(outs[True][0][k].cpu().numpy(), outs[False][0][k].cpu().numpy()) < 1e-4, k
+    assert O.rel_err(outs[True][1].cpu().numpy(), outs[False][1].cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("C", [1, 3])
+def test_motion_prologue_kernels_bit_exact(cuda, C):
+    """gray_difference_frames / gray_difference_pair (tai.py:67-74; mcnet.py:439-447; util.py:22-41): bit-identical
+    to the reference's elementwise chain evaluated op by op in FP32, close to the float64 oracle, adjoint exact."""
+    import torch
+    from video_frame_inpainting_b200 import ops
+    from video_frame_inpainting_b200.util.util import bgr2gray, bgr2gray_batched, inverse_transform
+    g = torch.Generator().manual_seed(11)
+    B, K, H, W = 3, 5, 20, 36
+    frames = (torch.rand(B, K, C, H, W, generator=g) * 2 - 1).cuda()
+
+    def chain(fr):                                    # tai.py:67-68 as the reference writes it
+        x = inverse_transform(fr)
+        gray = bgr2gray_batched(x) if C == 3 else x
+        return gray[:, 1:] - gray[:, :-1]
+    for reverse in (False, True):
+        ref = chain(torch.flip(frames, dims=[1]) if reverse else frames)
+        got = ops.gray_difference_frames(frames, reverse)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+    x64 = O.inverse_transform(frames.cpu().numpy())
+    gray64 = O.bgr2gray(x64, axis=2) if C == 3 else x64
+    assert_close(ops.gray_difference_frames(frames).cpu().numpy(), gray64[:, 1:] - gray64[:, :-1], tol=1e-5, what="gray diff")
+    a = (torch.rand(B, C, H, W, generator=g) * 2 - 1).cuda().requires_grad_(True)
+    b = (torch.rand(B, C, H, W, generator=g) * 2 - 1).cuda().requires_grad_(True)
+    gray01 = lambda v: bgr2gray(inverse_transform(v)) if C == 3 else inverse_transform(v)   # mcnet.py:439-447
+    ref = gray01(a) - gray01(b)
+    got = ops.GrayDiffPairFunction.apply(a, b)
+    assert torch.equal(got.detach(), ref.detach())
+    w = torch.rand(ref.shape, generator=g).cuda()
+    ga_ref, gb_ref = torch.autograd.grad((ref * w).sum(), (a, b))
+    ga, gb = torch.autograd.grad((got * w).sum(), (a, b))
+    assert O.rel_err(ga.cpu().numpy(), ga_ref.cpu().numpy()) < 1e-6 and O.rel_err(gb.cpu().numpy(), gb_ref.cpu().numpy()) < 1e-6
 
 
 def test_frames_to_uint8_and_png_layout(cuda, tmp_path):

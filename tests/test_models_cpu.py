@@ -138,6 +138,27 @@ def test_reference_model_classes_golden(ci):
         assert O.rel_err(params[str(n)].grad.numpy(), z[tag + 'grad_' + str(n)]) < 1e-4, n
 
 
+def test_reference_full_configuration_golden_forward():
+    """tests/golden/tai_full_config_ref.npz: the reference's own TAIFillInModel(64, 1, 3, 51, num_block=5) -- the
+    network registered as TAI_gray (create_model.py:27-28) -- on one 64x64 clip, K = F = T = 5, with weights that are
+    a function of the state_dict key names (tests/helpers.py:name_seeded_state_dict; 38.3 M parameters cannot be
+    committed).  Here: same keys in the same order, and the CPU port reproduces the five outputs to 1e-5 (forward
+    only: the backward pass is another 80 s of CPU time; gradients are checked on the GPU, test_models_gpu.py)."""
+    import os
+    from tests.helpers import name_seeded_state_dict
+    from video_frame_inpainting_b200.models.create_model import create_model
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_full_config_ref.npz"))
+    model = create_model('TAI_gray')
+    assert list(model.state_dict().keys()) == [str(n) for n in z['sd_names']]
+    model.load_state_dict(name_seeded_state_dict(model.state_dict()), strict=True)
+    model = to_cpu_reference(model)
+    with torch.no_grad():
+        out = model(int(z['cfg_T']), torch.from_numpy(z['pre']), torch.from_numpy(z['fol']))
+    for k in ('pred', 'pred_forward', 'pred_backward', 'interp_net_outputs_1', 'interp_net_outputs_2'):
+        assert out[k].shape == z['out_' + k].shape
+        assert O.rel_err(out[k].numpy(), z['out_' + k]) < 1e-5, k
+
+
 def test_reference_slomo_classes_golden():
     """Same pin for the Super SloMo baseline (the reference's own slomo.py classes): strict state_dict load, the
     five outputs (incl. the reversed time order of the collectors, slomo.py:331-340) and a gradient."""

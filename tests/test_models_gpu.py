@@ -217,6 +217,30 @@ def test_gpu_model_matches_reference_classes_golden(cuda, ci):
         assert O.rel_err(params[str(n)].grad.cpu().numpy(), z[tag + 'grad_' + str(n)]) < 2e-2, n
 
 
+def test_gpu_model_matches_reference_full_configuration_golden(cuda):
+    """The registered TAI_gray network (gf 64, ks 51, five kernel-network blocks; create_model.py:27-28) on the GPU
+    against outputs and gradients of the reference's own classes (tests/golden/tai_full_config_ref.npz, made by
+    tests/golden/make_full_config_golden.py; weights re-created from the key names).  Outputs are O(1e-2): the
+    bar is 5e-4 of max(|ref|, rms) -- cuDNN's FP32 convolutions against torch's CPU ones through ~70 layers."""
+    import os
+    from tests.helpers import name_seeded_state_dict
+    from video_frame_inpainting_b200.models.create_model import create_model
+    _strict_fp32()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tai_full_config_ref.npz"))
+    model = create_model('TAI_gray')
+    assert list(model.state_dict().keys()) == [str(n) for n in z['sd_names']]
+    model.load_state_dict(name_seeded_state_dict(model.state_dict()), strict=True)
+    model = model.cuda()
+    out = model(int(z['cfg_T']), torch.from_numpy(z['pre']).cuda(), torch.from_numpy(z['fol']).cuda())
+    for k in ('pred', 'pred_forward', 'pred_backward', 'interp_net_outputs_1', 'interp_net_outputs_2'):
+        assert O.rel_err(out[k].detach().cpu().numpy(), z['out_' + k]) < 5e-4, k
+    (out['pred'].pow(2).mean() + out['pred_forward'].mean() + out['pred_backward'].pow(2).mean()).backward()
+    params = dict(model.named_parameters())
+    for n in z['grad_names']:
+        g = params[str(n)].grad.cpu().numpy()
+        assert O.rel_err(g.reshape(g.shape[0], -1)[:8], z['grad_' + str(n)]) < 2e-3, n
+
+
 def test_gpu_slomo_matches_reference_classes_golden(cuda):
     """Super SloMo on the GPU (fused flow-combine / warp / refine / blend kernels in eval mode, FlowWarper kernel
     with autograd in train mode) against outputs of the reference's own slomo.py classes."""

@@ -13,7 +13,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from video_frame_inpainting_b200 import ops  # noqa: E402
+from video_frame_inpainting_b200 import _lib, ops  # noqa: E402
 from tools.kernel_bench import timeit  # noqa: E402
 
 
@@ -39,12 +39,14 @@ def main():
     batches = (1, 16) if args.quick else (1, 4, 16, 64)
     out = open(args.out, "w", newline="") if args.out else sys.stdout
     w = csv.writer(out)
-    w.writerow(["ks", "size", "B", "C", "kernel", "ms", "tflops", "gbs", "frac_fma_peak", "frac_hbm", "bound",
+    w.writerow(["ks", "size", "B", "C", "kernel", "path", "ms", "tflops", "gbs", "frac_fma_peak", "frac_hbm", "bound",
                 "frac_of_bound"])
-    for ks in ks_list:
-        for S in sizes:
-            for B in batches:
-                for C in (1, 3):
+    extra = [] if args.quick else [(51, 126, 16, 1), (25, 130, 16, 3)]   # W % 4 != 0: the LDG-fed (non-TMA) kernels
+    grid = [(ks, S, B, C) for ks in ks_list for S in sizes for B in batches for C in (1, 3)] + extra
+    for (ks, S, B, C) in grid:
+        for _once in (0,):
+            for _once2 in (0,):
+                for _once3 in (0,):
                     if B * ks * S * S * 4 * 4 > 40e9:   # four kernel-map sized tensors must fit comfortably
                         continue
                     I = U(B, C, S + ks - 1, S + ks - 1)
@@ -59,9 +61,15 @@ def main():
                     }
                     for name, (fn, flops, by) in cases.items():
                         med, _ = timeit(fn, iters=args.iters, warm=2, flush=flush)
+                        path = _lib.last_path()
+                        if name == "bwd":      # two launchers ran: ask each for its kernel family (untimed)
+                            ops.sepconv_backward(gO, I, V, H, ks, (False, True, True))
+                            path = _lib.last_path()
+                            ops.sepconv_backward(gO, I, V, H, ks, (True, False, False))
+                            path += "+" + _lib.last_path()
                         bound_t = max(flops / p_fma, by / bw)
                         bound = "fma" if flops / p_fma >= by / bw else "hbm"
-                        w.writerow([ks, S, B, C, name, "%.4f" % (med * 1e3), "%.2f" % (flops / med / 1e12),
+                        w.writerow([ks, S, B, C, name, path, "%.4f" % (med * 1e3), "%.2f" % (flops / med / 1e12),
                                     "%.0f" % (by / med / 1e9), "%.3f" % (flops / med / p_fma), "%.3f" % (by / med / bw),
                                     bound, "%.3f" % (bound_t / med)])
                         out.flush()

@@ -21,6 +21,7 @@ SIGNATURES = {
     "tai_b200_abi_version": (_c_i, []),
     "tai_b200_last_error": (ctypes.c_char_p, []),
     "tai_b200_launch_count": (ctypes.c_longlong, []),
+    "tai_b200_last_path": (ctypes.c_char_p, []),
     "tai_b200_timing_enable": (_c_i, [_c_i]),
     "tai_b200_timing_report": (_c_i, [ctypes.c_char_p, _c_i]),
     "SeparableConvolution_cuda_forward_b200": (_c_i, [_c_f] * 4 + [_c_i] * 5 + [_c_s]),
@@ -36,6 +37,10 @@ SIGNATURES = {
     "flow_warp_backward_b200": (_c_i, [_c_f] * 5 + [_c_i] * 4 + [_c_s]),
     "slomo_flow_combine_warp_forward_b200": (_c_i, [_c_f] * 4 + [ctypes.c_double] + [_c_f] * 4 + [_c_i] * 4 + [_c_s]),
     "slomo_refine_blend_forward_b200": (_c_i, [_c_f] * 7 + [ctypes.c_double] + [_c_f] + [_c_i] * 4 + [_c_s]),
+    "slomo_interp_input_forward_b200": (_c_i, [_c_f] * 7 + [_c_i] * 5 + [_c_s]),
+    "slomo_interp_input_backward_b200": (_c_i, [_c_f] * 9 + [_c_i] * 5 + [_c_s]),
+    "slomo_refine_blend_batched_forward_b200": (_c_i, [_c_f] * 8 + [_c_i] * 5 + [_c_s]),
+    "slomo_refine_blend_batched_backward_b200": (_c_i, [_c_f] * 13 + [_c_i] * 5 + [_c_s]),
     "upsample_bilinear2x_forward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "upsample_bilinear2x_backward_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
     "unpool_add_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 2 + [_c_s]),
@@ -49,6 +54,9 @@ SIGNATURES = {
     "bias_act_backward_workspace_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _c_i]),
     "bias_act_backward_b200": (_c_i, [_c_f] * 5 + [ctypes.c_longlong] + [_c_i] * 3 + [ctypes.c_float, _c_s]),
     "l2_normalize_b200": (_c_i, [_c_f] * 2 + [_c_i, ctypes.c_float, _c_s]),
+    "gray_difference_frames_b200": (_c_i, [_c_f] * 2 + [_c_i] * 6 + [_c_s]),
+    "gray_difference_pair_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 3 + [_c_s]),
+    "gray_difference_pair_backward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 3 + [_c_s]),
     "frames_to_uint8_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 4 + [_c_s]),
     "tai_b200_ffma_probe": (_c_i, [_c_f] + [_c_i] * 4 + [_c_s]),
 }
@@ -112,6 +120,11 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().tai_b200_launch_count())
+
+
+def last_path() -> str:
+    """Kernel family of this thread's last separable-convolution launch ("fwd:v3", "bwd_i:v4", "fwd:tiled", ...)."""
+    return (load().tai_b200_last_path() or b"").decode()
 
 
 def timing_enable(on: bool) -> None:

@@ -30,7 +30,9 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC",
-    # no --use_fast_math: the gate kernels need accurate expf/tanhf and the warp needs IEEE division
+    # no --use_fast_math: the warp / blend kernels rely on IEEE rounding of every operation (floor() of the
+    # coordinate chain is bit-exact against the FP32 reference) and the separable convolutions on plain FMA;
+    # the gate kernels pick their own approximations explicitly (ex2.approx / rcp.approx, elementwise.cu)
 ]
 
 
@@ -73,6 +75,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     if not force and is_up_to_date():
         return LIB_PATH
     nvcc = _nvcc()
+    started_from = source_hash()   # recorded at the end: an edit DURING the build leaves the library marked stale
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     hdr_mtime = max([os.path.getmtime(p) for p in glob.glob(os.path.join(CSRC, "*.cuh")) +
@@ -102,7 +105,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
     os.replace(tmp, LIB_PATH)
     with open(HASH_PATH, "w") as f:
-        f.write(source_hash() + "\n")
+        f.write(started_from + "\n")
     return LIB_PATH
 
 

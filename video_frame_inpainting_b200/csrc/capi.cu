@@ -24,6 +24,9 @@ void set_error(const char *fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static thread_local const char *g_path = "";
+void note_path(const char *path) { g_path = path; }
+
 // ---- per-kernel timing ---------------------------------------------------------------------------
 struct TimingRecord {
     std::string name;
@@ -59,6 +62,7 @@ void timing_end(cudaStream_t st)
 extern "C" int tai_b200_abi_version(void) { return TAI_B200_ABI_VERSION; }
 extern "C" const char *tai_b200_last_error(void) { return tai::g_err; }
 extern "C" long long tai_b200_launch_count(void) { return tai::g_launches.load(std::memory_order_relaxed); }
+extern "C" const char *tai_b200_last_path(void) { return tai::g_path; }
 
 extern "C" int tai_b200_timing_enable(int on)
 {

@@ -18,6 +18,9 @@ namespace tai {
 // ---- error plumbing (definitions in capi.cu) ------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// which kernel family a separable-convolution launcher chose ("fwd:v3", "bwd_i:v4", "fwd:tiled", ...): read back
+// through tai_b200_last_path() by the op sweep
+void note_path(const char *path);
 
 // Optional per-kernel timing (CUDA events on the launching stream), switched on by bench.py through
 // tai_b200_timing_enable().  `flops` / `bytes` are the ALGORITHMIC work of the launch.

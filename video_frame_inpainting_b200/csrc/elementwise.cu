@@ -2,22 +2,10 @@
 // warp, SloMo flow-combine / refine-blend fusions, and the FFMA probe used by bench.py.
 // Every kernel streams its operands exactly once with 128-bit accesses where alignment allows.
 #include "common.cuh"
+#include "warp.cuh"
 
 namespace tai {
 
-static inline unsigned stream_grid(long work_items, int block)
-{
-    long g = (work_items + block - 1) / block;
-    const long cap = (long)sm_count() * 8;  // 8 resident 256-thread CTAs per SM, grid-stride beyond
-    if (g > cap) {
-        // every thread makes the same number of grid-stride trips (a grid of exactly `cap` CTAs leaves a ragged
-        // second trip: 2048 CTAs of work on 1184 slots ran as 1 + 0.73 waves)
-        const long trips = (g + cap - 1) / cap;
-        g = (g + trips - 1) / trips;
-    }
-    if (g < 1) g = 1;
-    return (unsigned)g;
-}
 
 // Grid for a grid-stride kernel whose loop handles `unroll` items per trip: every thread makes the same number
 // of trips (a multiple of `unroll`), and the grid fits the kernel's real residency (occupancy query, cached by
@@ -197,94 +185,6 @@ gates_bwd_kernel(const float *__restrict__ conv, const float *__restrict__ state
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Bilinear backward warp (slomo.py:265-286 + torch-0.3.1 grid_sample: bilinear, zero padding).
-// The coordinate chain is evaluated with one IEEE rounding per reference operation (no FMA
-// contraction) so that floor() -- the integer part of the op -- matches the FP32 reference exactly:
-//   X = x + u;  g = 2*(X/W - 0.5);  ix = ((g + 1)/2)*(W-1)
-struct WarpCoord {
-    int x0, y0;
-    float ix, iy;
-};
-
-// Correctly rounded a / b from the correctly rounded reciprocal y = RN(1 / b) (formed once on the host):
-// q = RN(a * y), r = a - b * q (exact in an FMA), result = RN(q + r * y)  [Markstein].  b is the image width or
-// height -- a small integer --, a is a pixel coordinate: the result equals IEEE division bit for bit (12 M
-// random and near-integer cases over 24 sizes checked against FP32 division: no mismatch), in 3 instructions
-// instead of the ~10 + slow-path call of __fdiv_rn.  The four divisions of the coordinate chain made the warp
-// kernels instruction-bound (~1000 SASS instructions per pixel at C = 3).
-__device__ __forceinline__ float div_by_size(float a, float b, float y)
-{
-    const float q = __fmul_rn(a, y);
-    const float r = __fmaf_rn(-b, q, a);
-    return __fmaf_rn(r, y, q);
-}
-
-__device__ __forceinline__ float warp_axis(float pos, float flow, float size, float rsize)
-{
-    const float X = __fadd_rn(pos, flow);
-    const float g = __fmul_rn(2.f, __fsub_rn(div_by_size(X, size, rsize), 0.5f));
-    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), size - 1.f);   // (g + 1) / 2: halving is exact
-}
-
-struct WarpGeom {
-    int W, H;
-    float fW, fH, rW, rH;  // rW = RN(1 / W), rH = RN(1 / H) (host, IEEE division)
-};
-
-static inline WarpGeom warp_geom(int H, int W)
-{
-    WarpGeom g;
-    g.W = W; g.H = H;
-    g.fW = (float)W; g.fH = (float)H;
-    g.rW = 1.0f / (float)W; g.rH = 1.0f / (float)H;
-    return g;
-}
-
-__device__ __forceinline__ WarpCoord warp_coord(int x, int y, float u, float v, const WarpGeom &g)
-{
-    WarpCoord c;
-    c.ix = warp_axis((float)x, u, g.fW, g.rW);
-    c.iy = warp_axis((float)y, v, g.fH, g.rH);
-    c.x0 = __float2int_rd(c.ix);
-    c.y0 = __float2int_rd(c.iy);
-    return c;
-}
-
-// The four taps of one sample point: offset of the north-west tap, validity of each tap (zero padding) and the
-// bilinear weights -- formed once per pixel and reused for every channel.
-struct Taps {
-    int o;
-    bool v00, v01, v10, v11;
-    float wnw, wne, wsw, wse;
-};
-
-__device__ __forceinline__ Taps make_taps(const WarpCoord &c, int H, int W)
-{
-    Taps t;
-    const float x1 = (float)(c.x0 + 1), y1 = (float)(c.y0 + 1), x0 = (float)c.x0, y0 = (float)c.y0;
-    t.wnw = (x1 - c.ix) * (y1 - c.iy);
-    t.wne = (c.ix - x0) * (y1 - c.iy);
-    t.wsw = (x1 - c.ix) * (c.iy - y0);
-    t.wse = (c.ix - x0) * (c.iy - y0);
-    const bool vx0 = (unsigned)c.x0 < (unsigned)W, vx1 = (unsigned)c.x0 + 1u < (unsigned)W;
-    const bool vy0 = (unsigned)c.y0 < (unsigned)H, vy1 = (unsigned)c.y0 + 1u < (unsigned)H;
-    t.v00 = vx0 && vy0; t.v01 = vx1 && vy0; t.v10 = vx0 && vy1; t.v11 = vx1 && vy1;
-    // the offset is only dereferenced where a tap is valid; clamping keeps the product inside int range
-    t.o = min(max(c.y0, -1), H) * W + min(max(c.x0, -1), W);
-    return t;
-}
-
-__device__ __forceinline__ float sample(const float *__restrict__ plane, const Taps &t, int W)
-{
-    const float *p = plane + t.o;
-    const float nw = t.v00 ? __ldg(p) : 0.f, ne = t.v01 ? __ldg(p + 1) : 0.f;
-    const float sw = t.v10 ? __ldg(p + W) : 0.f, se = t.v11 ? __ldg(p + W + 1) : 0.f;
-    return nw * t.wnw + ne * t.wne + sw * t.wsw + se * t.wse;
-}
-
-// C == 0: runtime channel count
-#define TAI_CH_LOOP(CT, C) _Pragma("unroll") for (int ch = 0; ch < ((CT) ? (CT) : (C)); ++ch)
 
 template <int CT>
 __global__ void __launch_bounds__(256)
@@ -435,6 +335,73 @@ slomo_refine_blend_kernel(const float *__restrict__ i0, const float *__restrict_
                 const float a0 = sample(i0 + base + (long)ch * hw, w0, W), a1 = sample(i1 + base + (long)ch * hw, w1, W);
                 out[base + (long)ch * hw + pix] = (k0 * a0 + k1 * a1) / norm;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Motion-stream prologue (tai.py:67-74; mcnet.py:439-447; util.py:22-41): frames in [-1, 1] -> [0, 1]
+// (inverse_transform: (x + 1.) / 2) -> gray (bgr2gray: 0.1140 B + 0.5870 G + 0.2989 R, left to right; one channel:
+// identity) -> temporal difference.  The reference spells this as 4-7 elementwise kernels per call over strided
+// slices; here it is one pass.  One rounding per reference operation (no FMA contraction), so the result is
+// bit-identical to the reference's FP32 chain.
+template <int C>
+__device__ __forceinline__ float gray01(const float *__restrict__ p, long cstride)
+{
+    if (C == 1) return __fmul_rn(__fadd_rn(ld_stream(p), 1.f), 0.5f);
+    const float b = __fmul_rn(__fadd_rn(ld_stream(p), 1.f), 0.5f);
+    const float g = __fmul_rn(__fadd_rn(ld_stream(p + cstride), 1.f), 0.5f);
+    const float r = __fmul_rn(__fadd_rn(ld_stream(p + 2 * cstride), 1.f), 0.5f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.1140f, b), __fmul_rn(0.5870f, g)), __fmul_rn(0.2989f, r));
+}
+
+// frames [B,K,C,HW] -> out [B,K-1,1,HW]: out[b,k] = gray01(frame i(k+1)) - gray01(frame i(k)), i(k) = k or K-1-k
+// (reverse: the time-reversed following frames of tai.py:71-74 without materialising the flip).  A thread walks
+// the K frames of one pixel, so every frame is read once.
+template <int C>
+__global__ void __launch_bounds__(256)
+gray_diff_frames_kernel(const float *__restrict__ frames, float *__restrict__ out, int B, int K, long hw, int reverse)
+{
+    const long n = (long)B * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / hw, pix = idx - b * hw;
+        const float *fb = frames + b * K * C * hw + pix;
+        float prev = gray01<C>(fb + (long)(reverse ? K - 1 : 0) * C * hw, hw);
+        for (int k = 1; k < K; ++k) {
+            const float cur = gray01<C>(fb + (long)(reverse ? K - 1 - k : k) * C * hw, hw);
+            out[(b * (K - 1) + (k - 1)) * hw + pix] = __fsub_rn(cur, prev);
+            prev = cur;
+        }
+    }
+}
+
+// a, b [N,C,HW] -> out [N,1,HW] = gray01(a) - gray01(b)   (mcnet.py:439-447: the next motion input)
+template <int C>
+__global__ void __launch_bounds__(256)
+gray_diff_pair_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long N, long hw)
+{
+    const long n = N * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long s = idx / hw, pix = idx - s * hw;
+        out[idx] = __fsub_rn(gray01<C>(a + s * C * hw + pix, hw), gray01<C>(b + s * C * hw + pix, hw));
+    }
+}
+
+// adjoint: ga[c] = 0.5 w_c g, gb[c] = -0.5 w_c g (w = 1 for one channel); either output may be null
+template <int C>
+__global__ void __launch_bounds__(256)
+gray_diff_pair_bwd_kernel(const float *__restrict__ gout, float *__restrict__ ga, float *__restrict__ gb, long N, long hw)
+{
+    const long n = N * hw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+        const long s = idx / hw, pix = idx - s * hw;
+        const float g = ld_stream(gout + idx);
+        const float w[3] = {C == 1 ? 1.f : 0.1140f, 0.5870f, 0.2989f};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float v = (g * w[c]) * 0.5f;
+            if (ga) ga[(s * C + c) * hw + pix] = v;
+            if (gb) gb[(s * C + c) * hw + pix] = -v;
         }
     }
 }
@@ -639,6 +606,57 @@ extern "C" int slomo_refine_blend_forward_b200(const float *i0, const float *i1,
     else
         slomo_refine_blend_kernel<0><<<grid, 256, 0, st>>>(i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, omt, ft, out, B, C, g);
     return check_launch("slomo_refine_blend_kernel");
+}
+
+extern "C" int gray_difference_frames_b200(const float *frames, float *out, int B, int K, int C, int H, int W, int reverse,
+                                           void *stream)
+{
+    TAI_REQUIRE(frames && out && B > 0 && K > 1 && (C == 1 || C == 3) && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT,
+                "gray_difference_frames_b200: bad arguments (B=%d K=%d C=%d H=%d W=%d; C must be 1 or 3, K >= 2)", B, K, C, H, W);
+    TAI_REQUIRE(fits_int31((long long)B * K * C * H * W), TAI_ERR_TOO_LARGE, "gray_difference_frames_b200: tensor has >= 2^31 elements");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long hw = (long)H * W;
+    TimingScope ts("gray_diff_frames", st, 0.0, 4.0 * ((double)K * C + (K - 1)) * B * hw);
+    const unsigned grid = stream_grid((long)B * hw, 256);
+    if (C == 3)
+        gray_diff_frames_kernel<3><<<grid, 256, 0, st>>>(frames, out, B, K, hw, reverse ? 1 : 0);
+    else
+        gray_diff_frames_kernel<1><<<grid, 256, 0, st>>>(frames, out, B, K, hw, reverse ? 1 : 0);
+    return check_launch("gray_diff_frames_kernel");
+}
+
+extern "C" int gray_difference_pair_forward_b200(const float *a, const float *b, float *out, long long N, int C, int H, int W,
+                                                 void *stream)
+{
+    TAI_REQUIRE(a && b && out && N > 0 && (C == 1 || C == 3) && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT,
+                "gray_difference_pair_forward_b200: bad arguments (C must be 1 or 3)");
+    TAI_REQUIRE(fits_int31(N * C * H * W), TAI_ERR_TOO_LARGE, "gray_difference_pair_forward_b200: tensor has >= 2^31 elements");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long hw = (long)H * W;
+    TimingScope ts("gray_diff_pair", st, 0.0, 4.0 * (2.0 * C + 1.0) * N * hw);
+    const unsigned grid = stream_grid((long)N * hw, 256);
+    if (C == 3)
+        gray_diff_pair_kernel<3><<<grid, 256, 0, st>>>(a, b, out, (long)N, hw);
+    else
+        gray_diff_pair_kernel<1><<<grid, 256, 0, st>>>(a, b, out, (long)N, hw);
+    return check_launch("gray_diff_pair_kernel");
+}
+
+extern "C" int gray_difference_pair_backward_b200(const float *grad_out, float *g_a, float *g_b, long long N, int C, int H, int W,
+                                                  void *stream)
+{
+    TAI_REQUIRE(grad_out && (g_a || g_b) && N > 0 && (C == 1 || C == 3) && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT,
+                "gray_difference_pair_backward_b200: bad arguments (C must be 1 or 3)");
+    TAI_REQUIRE(fits_int31(N * C * H * W), TAI_ERR_TOO_LARGE, "gray_difference_pair_backward_b200: tensor has >= 2^31 elements");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long hw = (long)H * W;
+    TimingScope ts("gray_diff_pair_bwd", st, 0.0, 4.0 * (1.0 + ((g_a ? 1.0 : 0.0) + (g_b ? 1.0 : 0.0)) * C) * N * hw);
+    const unsigned grid = stream_grid((long)N * hw, 256);
+    if (C == 3)
+        gray_diff_pair_bwd_kernel<3><<<grid, 256, 0, st>>>(grad_out, g_a, g_b, (long)N, hw);
+    else
+        gray_diff_pair_bwd_kernel<1><<<grid, 256, 0, st>>>(grad_out, g_a, g_b, (long)N, hw);
+    return check_launch("gray_diff_pair_bwd_kernel");
 }
 
 extern "C" int frames_to_uint8_b200(const float *frames, unsigned char *out, long long N, int C, int H, int W, int flip_channels,

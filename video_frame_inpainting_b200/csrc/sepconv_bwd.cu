@@ -422,6 +422,7 @@ static int launch_vh_tiled(const BwdParams &p0, cudaStream_t st)
         TimingScope ts("sepconv_bwd_vh", st, fl, by);
         kern<<<(unsigned)((long)p.B * p.nty * p.ntx), 32 * WX * WY, smem, st>>>(p);
     }
+    note_path("bwd_vh:tiled");
     return check_launch("sepconv_bwd_vh_kernel");
 }
 
@@ -451,6 +452,7 @@ static int launch_vh_v3(const BwdParams &p0, cudaStream_t st)
         TimingScope ts("sepconv_bwd_vh", st, fl, by);
         kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
     }
+    note_path("bwd_vh:v3");
     return check_launch("sepconv_bwd_vh_v3_kernel");
 }
 
@@ -473,6 +475,7 @@ static int launch_vh(const BwdParams &p, cudaStream_t st)
             TimingScope ts("sepconv_bwd_vh", st, fl, by);
             sepconv_bwd_vh_simple_kernel<PAD><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
         }
+        note_path("bwd_vh:simple");
         return check_launch("sepconv_bwd_vh_simple_kernel");
     }
     {
@@ -531,6 +534,7 @@ static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
         TimingScope ts("sepconv_bwd_i", st, fl, by);
         kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
     }
+    note_path("bwd_i:v3");
     return check_launch("sepconv_bwd_i_v3_kernel");
 }
 
@@ -566,6 +570,7 @@ static int launch_gi_v4(const BwdParams &p0, cudaStream_t st)
         TimingScope ts("sepconv_bwd_i", st, fl, by);
         kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
     }
+    note_path("bwd_i:v4");
     return check_launch("sepconv_bwd_i_v4_kernel");
 }
 
@@ -602,6 +607,7 @@ static int launch_gi(const BwdParams &p, cudaStream_t st)
             else
                 sepconv_bwd_i_kernel<3><<<grid, 128, 0, st>>>(p);
         }
+        note_path("bwd_i:gather");
         return check_launch("sepconv_bwd_i_kernel");
     }
     const long n = (long)p.B * p.C * Hi * Wi;
@@ -611,6 +617,7 @@ static int launch_gi(const BwdParams &p, cudaStream_t st)
         TimingScope ts("sepconv_bwd_i", st, fl, by);
         sepconv_bwd_i_simple_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p);
     }
+    note_path("bwd_i:simple");
     return check_launch("sepconv_bwd_i_simple_kernel");
 }
 

@@ -271,6 +271,7 @@ static int launch_fwd_tiled(const FwdParams &p0, cudaStream_t st)
         TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
         kern<<<(unsigned)blocks, 32 * WX * WY, smem, st>>>(p);
     }
+    note_path("fwd:tiled");
     return check_launch("sepconv_fwd_kernel");
 }
 
@@ -307,6 +308,7 @@ static int launch_fwd_v3(const FwdParams &p0, cudaStream_t st)
         TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
         kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
     }
+    note_path("fwd:v3");
     return check_launch("sepconv_fwd_v3_kernel");
 }
 
@@ -352,6 +354,7 @@ static int launch_fwd_v5(const FwdParams &p0, cudaStream_t st)
         TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
         kern<<<(unsigned)(nsm * cps), Cfg::NT, smem, st>>>(maps, p, cps);
     }
+    note_path("fwd:v5");
     return check_launch("sepconv_fwd_v5_kernel");
 }
 
@@ -370,6 +373,7 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
             TimingScope ts(DUAL ? "sepconv_fused_fwd" : "sepconv_fwd", st, fl, by);
             sepconv_fwd_simple_kernel<PAD, DUAL><<<(unsigned)(grid < 1 ? 1 : grid), block, 0, st>>>(p);
         }
+        note_path("fwd:simple");
         return check_launch("sepconv_fwd_simple_kernel");
     }
     if (p.Ho >= FP) {

@@ -1,0 +1,466 @@
+// Super SloMo intermediate-frame stages (slomo.py:307-340) for sm_100a, ALL T time steps per launch, with their
+// adjoints.
+//
+// The reference runs, per middle frame t: two scalar-tensor flow combinations (slomo.py:313-314), two
+// FlowWarper calls (315-316: host meshgrid + H2D copy + ~8 elementwise kernels + grid_sample each), a torch.cat of
+// six tensors (318), the refinement U-Net, two clamps, two more FlowWarper calls and ~10 elementwise kernels for the
+// visibility blend (320-328).  The T time steps do not depend on each other (the U-Nets carry no state), so here
+// they are one batch:
+//
+//   slomo_interp_input   F_t0, F_t1 for every t, both warps, and the refinement network's input tensor
+//                        X[t*B+b] = cat(I0, g(I0,F_t0), F_t0, F_t1, g(I1,F_t1), I1) written in place (no cat
+//                        copy); the flows also go to the model's F_t_*_collector outputs in the reference's
+//                        (reversed) time order, which is where the blend stage reads them;
+//   slomo_refine_blend   refine-add-clamp, two warps, visibility-weighted blend, result written straight into
+//                        pred[B,T,C,H,W] (reversed time order, slomo.py:332-340);
+//   *_bwd                the adjoints w.r.t. the flows / refinements / visibility: pure gathers (the warp's flow
+//                        gradient needs the same four taps as the forward), one thread per pixel accumulating
+//                        over the T time steps -- no atomics, deterministic.  Image gradients (I0 / I1 are
+//                        network inputs) are not produced here; a caller that needs them takes the composed route
+//                        through flow_warp_backward_b200.
+//
+// All four are HBM-bound gather / stream kernels; at T*B = 24 UCF frames a launch moves 150-250 MB instead of
+// the 20-50 MB of the per-t kernels, which is what lifts them from launch-latency-bound to bandwidth-bound.
+#include "common.cuh"
+#include "warp.cuh"
+
+namespace tai {
+
+constexpr int kSlomoMaxT = 16;
+
+// Python-float (double) scalars of slomo.py:312-314,325-328, rounded to FP32 where they meet a tensor.
+struct SlomoTimes {
+    int T;
+    float c00[kSlomoMaxT], c01[kSlomoMaxT], c10[kSlomoMaxT], c11[kSlomoMaxT], omt[kSlomoMaxT], t[kSlomoMaxT];
+};
+
+static SlomoTimes slomo_times(int T)
+{
+    SlomoTimes tm;
+    tm.T = T;
+    for (int i = 0; i < kSlomoMaxT; ++i) {
+        const double t = (i + 1.0) / (T + 1.0);  // t = (t_ + 1) / (T + 1), true division (slomo.py:2,312)
+        tm.c00[i] = (float)(-(1.0 - t) * t);
+        tm.c01[i] = (float)(t * t);
+        tm.c10[i] = (float)((1.0 - t) * (1.0 - t));
+        tm.c11[i] = (float)(t * (1.0 - t));
+        tm.omt[i] = (float)(1.0 - t);
+        tm.t[i] = (float)t;
+    }
+    return tm;
+}
+
+struct TFlows {
+    float t0u, t0v, t1u, t1v;
+};
+
+// same association as the reference: (coef * F01) + (coef * F10), one rounding per operation, no contraction
+__device__ __forceinline__ TFlows combine_flows(const SlomoTimes &tm, int t, float a_u, float a_v, float b_u, float b_v)
+{
+    TFlows f;
+    f.t0u = __fadd_rn(__fmul_rn(tm.c00[t], a_u), __fmul_rn(tm.c01[t], b_u));
+    f.t0v = __fadd_rn(__fmul_rn(tm.c00[t], a_v), __fmul_rn(tm.c01[t], b_v));
+    f.t1u = __fsub_rn(__fmul_rn(tm.c10[t], a_u), __fmul_rn(tm.c11[t], b_u));
+    f.t1v = __fsub_rn(__fmul_rn(tm.c10[t], a_v), __fmul_rn(tm.c11[t], b_v));
+    return f;
+}
+
+// The four taps of a sample point and the derivative of the bilinear interpolant w.r.t. the sampling position.
+struct TapVals {
+    float val, ddx, ddy;
+};
+
+__device__ __forceinline__ TapVals sample_with_derivative(const float *__restrict__ plane, const Taps &t, int W,
+                                                          float ax, float bx, float ay, float by)
+{
+    const float *p = plane + t.o;
+    const float nw = t.v00 ? __ldg(p) : 0.f, ne = t.v01 ? __ldg(p + 1) : 0.f;
+    const float sw = t.v10 ? __ldg(p + W) : 0.f, se = t.v11 ? __ldg(p + W + 1) : 0.f;
+    TapVals r;
+    r.val = nw * t.wnw + ne * t.wne + sw * t.wsw + se * t.wse;
+    r.ddx = (ne - nw) * ay + (se - sw) * by;
+    r.ddy = (sw - nw) * ax + (se - ne) * bx;
+    return r;
+}
+
+struct Frac {
+    float ax, bx, ay, by;  // x1 - ix, ix - x0, y1 - iy, iy - y0
+};
+__device__ __forceinline__ Frac frac_of(const WarpCoord &c)
+{
+    Frac f;
+    f.ax = (float)(c.x0 + 1) - c.ix;
+    f.bx = c.ix - (float)c.x0;
+    f.ay = (float)(c.y0 + 1) - c.iy;
+    f.by = c.iy - (float)c.y0;
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slomo.py:312-318 for every t: thread = (b, pixel), loop over the T time steps (the flows and the two direct
+// image pixels are loaded once).
+template <int CT>
+__global__ void __launch_bounds__(256)
+slomo_interp_input_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                          const float *__restrict__ f01, const float *__restrict__ f10, const SlomoTimes tm,
+                          float *__restrict__ X, float *__restrict__ ft0c, float *__restrict__ ft1c,
+                          int B, int C, const WarpGeom g)
+{
+    const int H = g.H, W = g.W, T = tm.T;
+    const int hw = H * W;
+    const int n = B * hw;
+    const int XC = 4 * C + 4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx / hw, pix = idx - b * hw;
+        const int y = pix / W, x = pix - y * W;
+        const long fu = (long)b * 2 * hw + pix, fv = fu + hw;
+        const float a_u = ld_stream(f01 + fu), a_v = ld_stream(f01 + fv);
+        const float b_u = ld_stream(f10 + fu), b_v = ld_stream(f10 + fv);
+        const long base = (long)b * C * hw;
+        float p0[CT ? CT : 1], p1[CT ? CT : 1];
+        if (CT) {
+            TAI_CH_LOOP(CT, C) {
+                p0[ch] = __ldg(i0 + base + (long)ch * hw + pix);
+                p1[ch] = __ldg(i1 + base + (long)ch * hw + pix);
+            }
+        }
+        for (int t = 0; t < T; ++t) {
+            const TFlows f = combine_flows(tm, t, a_u, a_v, b_u, b_v);
+            const Taps w0 = make_taps(warp_coord(x, y, f.t0u, f.t0v, g), H, W);
+            const Taps w1 = make_taps(warp_coord(x, y, f.t1u, f.t1v, g), H, W);
+            float *xo = X + ((long)t * B + b) * XC * hw + pix;
+            const long fo = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;   // collectors: reversed time order
+            if (CT) {
+                float r0[CT ? CT : 1], r1[CT ? CT : 1];
+                TAI_CH_LOOP(CT, C) {   // all gathers in flight before the first store
+                    r0[ch] = sample(i0 + base + (long)ch * hw, w0, W);
+                    r1[ch] = sample(i1 + base + (long)ch * hw, w1, W);
+                }
+                TAI_CH_LOOP(CT, C) {
+                    xo[(long)ch * hw] = p0[ch];
+                    xo[(long)(C + ch) * hw] = r0[ch];
+                    xo[(long)(2 * C + 4 + ch) * hw] = r1[ch];
+                    xo[(long)(3 * C + 4 + ch) * hw] = p1[ch];
+                }
+            } else {
+                for (int ch = 0; ch < C; ++ch) {
+                    xo[(long)ch * hw] = __ldg(i0 + base + (long)ch * hw + pix);
+                    xo[(long)(C + ch) * hw] = sample(i0 + base + (long)ch * hw, w0, W);
+                    xo[(long)(2 * C + 4 + ch) * hw] = sample(i1 + base + (long)ch * hw, w1, W);
+                    xo[(long)(3 * C + 4 + ch) * hw] = __ldg(i1 + base + (long)ch * hw + pix);
+                }
+            }
+            xo[(long)(2 * C) * hw] = f.t0u;
+            xo[(long)(2 * C + 1) * hw] = f.t0v;
+            xo[(long)(2 * C + 2) * hw] = f.t1u;
+            xo[(long)(2 * C + 3) * hw] = f.t1v;
+            ft0c[fo] = f.t0u;
+            ft0c[fo + hw] = f.t0v;
+            ft1c[fo] = f.t1u;
+            ft1c[fo + hw] = f.t1v;
+        }
+    }
+}
+
+// Adjoint w.r.t. F_0_1 and F_1_0: for every t the gradient reaching F_t0 is (flow gradient of the warp of I0)
+// + (gradient of X's F_t0 channels) + (gradient of the collector), likewise F_t1; the linear combination of
+// slomo.py:313-314 is transposed and summed over t in registers.
+template <int CT>
+__global__ void __launch_bounds__(256)
+slomo_interp_input_bwd_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                              const float *__restrict__ f01, const float *__restrict__ f10, const SlomoTimes tm,
+                              const float *__restrict__ gX, const float *__restrict__ gft0c,
+                              const float *__restrict__ gft1c, float *__restrict__ gf01, float *__restrict__ gf10,
+                              int B, int C, const WarpGeom g)
+{
+    const int H = g.H, W = g.W, T = tm.T;
+    const int hw = H * W;
+    const int n = B * hw;
+    const int XC = 4 * C + 4;
+    const float sx = (float)(W - 1) / (float)W, sy = (float)(H - 1) / (float)H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx / hw, pix = idx - b * hw;
+        const int y = pix / W, x = pix - y * W;
+        const long fu = (long)b * 2 * hw + pix, fv = fu + hw;
+        const float a_u = ld_stream(f01 + fu), a_v = ld_stream(f01 + fv);
+        const float b_u = ld_stream(f10 + fu), b_v = ld_stream(f10 + fv);
+        const long base = (long)b * C * hw;
+        float gau = 0.f, gav = 0.f, gbu = 0.f, gbv = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const TFlows f = combine_flows(tm, t, a_u, a_v, b_u, b_v);
+            const WarpCoord c0 = warp_coord(x, y, f.t0u, f.t0v, g), c1 = warp_coord(x, y, f.t1u, f.t1v, g);
+            const Taps w0 = make_taps(c0, H, W), w1 = make_taps(c1, H, W);
+            const Frac q0 = frac_of(c0), q1 = frac_of(c1);
+            const float *gxo = gX + ((long)t * B + b) * XC * hw + pix;
+            float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f;
+            TAI_CH_LOOP(CT, C) {
+                const float go0 = ld_stream(gxo + (long)(C + ch) * hw), go1 = ld_stream(gxo + (long)(2 * C + 4 + ch) * hw);
+                const TapVals s0 = sample_with_derivative(i0 + base + (long)ch * hw, w0, W, q0.ax, q0.bx, q0.ay, q0.by);
+                const TapVals s1 = sample_with_derivative(i1 + base + (long)ch * hw, w1, W, q1.ax, q1.bx, q1.ay, q1.by);
+                gx0 += go0 * s0.ddx;
+                gy0 += go0 * s0.ddy;
+                gx1 += go1 * s1.ddx;
+                gy1 += go1 * s1.ddy;
+            }
+            float g0u = gx0 * sx + ld_stream(gxo + (long)(2 * C) * hw);
+            float g0v = gy0 * sy + ld_stream(gxo + (long)(2 * C + 1) * hw);
+            float g1u = gx1 * sx + ld_stream(gxo + (long)(2 * C + 2) * hw);
+            float g1v = gy1 * sy + ld_stream(gxo + (long)(2 * C + 3) * hw);
+            const long fo = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;
+            if (gft0c) {
+                g0u += ld_stream(gft0c + fo);
+                g0v += ld_stream(gft0c + fo + hw);
+            }
+            if (gft1c) {
+                g1u += ld_stream(gft1c + fo);
+                g1v += ld_stream(gft1c + fo + hw);
+            }
+            // F_t0 = c00 F01 + c01 F10 ; F_t1 = c10 F01 - c11 F10
+            gau += tm.c00[t] * g0u + tm.c10[t] * g1u;
+            gav += tm.c00[t] * g0v + tm.c10[t] * g1v;
+            gbu += tm.c01[t] * g0u - tm.c11[t] * g1u;
+            gbv += tm.c01[t] * g0v - tm.c11[t] * g1v;
+        }
+        gf01[fu] = gau;
+        gf01[fv] = gav;
+        gf10[fu] = gbu;
+        gf10[fv] = gbv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slomo.py:320-328 for every (t, b): thread = (b, pixel), loop over t with the NEXT time step's nine streamed
+// operands already in flight (a thread per (t, b, pixel) ran at 45 % of the HBM peak: two dependent memory round
+// trips -- streamed operands, then the gathers they address -- per thread and only ~24 resident warps per SM to
+// hide them; the loop overlaps the first trip of t+1 with the gathers and stores of t).
+__device__ __forceinline__ float clamp_pm1(float v) { return fminf(fmaxf(v, -1.f), 1.f); }
+
+struct RefineIn {
+    float d0u, d0v, d1u, d1v, f0u, f0v, f1u, f1v, vis;
+};
+
+__device__ __forceinline__ RefineIn refine_load(const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                                                const float *__restrict__ d0, const float *__restrict__ d1,
+                                                const float *__restrict__ v0, int t, int b, int pix, int B, int T, int hw)
+{
+    const long nb = (long)t * B + b;
+    const long du = nb * 2 * hw + pix, fu = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;  // collectors: reversed time
+    RefineIn r;
+    r.d0u = ld_stream(d0 + du); r.d0v = ld_stream(d0 + du + hw);
+    r.d1u = ld_stream(d1 + du); r.d1v = ld_stream(d1 + du + hw);
+    r.f0u = ld_stream(ft0c + fu); r.f0v = ld_stream(ft0c + fu + hw);
+    r.f1u = ld_stream(ft1c + fu); r.f1v = ld_stream(ft1c + fu + hw);
+    r.vis = ld_stream(v0 + nb * hw + pix);
+    return r;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256)
+slomo_refine_blend_t_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                            const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                            const float *__restrict__ d0, const float *__restrict__ d1, const float *__restrict__ v0,
+                            const SlomoTimes tm, float *__restrict__ pred, int B, int C, const WarpGeom g)
+{
+    const int H = g.H, W = g.W, T = tm.T;
+    const int hw = H * W;
+    const int n = B * hw;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx / hw, pix = idx - b * hw;
+        const int y = pix / W, x = pix - y * W;
+        const long base = (long)b * C * hw;
+        RefineIn cur = refine_load(ft0c, ft1c, d0, d1, v0, 0, b, pix, B, T, hw);
+        for (int t = 0; t < T; ++t) {
+            RefineIn nxt = cur;
+            if (t + 1 < T) nxt = refine_load(ft0c, ft1c, d0, d1, v0, t + 1, b, pix, B, T, hw);
+            const float r0u = clamp_pm1(__fadd_rn(cur.d0u, cur.f0u)), r0v = clamp_pm1(__fadd_rn(cur.d0v, cur.f0v));
+            const float r1u = clamp_pm1(__fadd_rn(cur.d1u, cur.f1u)), r1v = clamp_pm1(__fadd_rn(cur.d1v, cur.f1v));
+            const Taps w0 = make_taps(warp_coord(x, y, r0u, r0v, g), H, W);
+            const Taps w1 = make_taps(warp_coord(x, y, r1u, r1v, g), H, W);
+            const float vis1 = 1.f - cur.vis;
+            const float k0 = tm.omt[t] * cur.vis, k1 = tm.t[t] * vis1;
+            const float norm = k0 + k1;
+            float *out = pred + ((long)b * T + (T - 1 - t)) * C * hw + pix;   // reversed time order (slomo.py:332-340)
+            if (CT) {
+                float a0[CT ? CT : 1], a1[CT ? CT : 1];
+                TAI_CH_LOOP(CT, C) {
+                    a0[ch] = sample(i0 + base + (long)ch * hw, w0, W);
+                    a1[ch] = sample(i1 + base + (long)ch * hw, w1, W);
+                }
+                TAI_CH_LOOP(CT, C) out[(long)ch * hw] = (k0 * a0[ch] + k1 * a1[ch]) / norm;
+            } else {
+                for (int ch = 0; ch < C; ++ch) {
+                    const float a0 = sample(i0 + base + (long)ch * hw, w0, W), a1 = sample(i1 + base + (long)ch * hw, w1, W);
+                    out[(long)ch * hw] = (k0 * a0 + k1 * a1) / norm;
+                }
+            }
+            cur = nxt;
+        }
+    }
+}
+
+// Adjoint w.r.t. the refined flows (the clamp passes gradient on [-1, 1] inclusive, as torch.clamp does; dF_t and
+// F_t enter through their sum, so they receive the same gradient) and the visibility map:
+//   out = (k0 a0 + k1 a1) / n,  k0 = (1-t) V,  k1 = t (1 - V),  n = k0 + k1
+//   d out / d V = ((1-t) a0 - t a1 - out ((1-t) - t)) / n
+template <int CT>
+__global__ void __launch_bounds__(256)
+slomo_refine_blend_t_bwd_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                                const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                                const float *__restrict__ d0, const float *__restrict__ d1,
+                                const float *__restrict__ v0, const SlomoTimes tm, const float *__restrict__ gpred,
+                                float *__restrict__ gft0c, float *__restrict__ gft1c, float *__restrict__ gd0,
+                                float *__restrict__ gd1, float *__restrict__ gv0, int B, int C, const WarpGeom g)
+{
+    const int H = g.H, W = g.W, T = tm.T;
+    const int hw = H * W;
+    const int n = B * hw;
+    const float sx = (float)(W - 1) / (float)W, sy = (float)(H - 1) / (float)H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int b = idx / hw, pix = idx - b * hw;
+        const int y = pix / W, x = pix - y * W;
+        const long base = (long)b * C * hw;
+        RefineIn cur = refine_load(ft0c, ft1c, d0, d1, v0, 0, b, pix, B, T, hw);
+        for (int t = 0; t < T; ++t) {
+            RefineIn nxt = cur;
+            if (t + 1 < T) nxt = refine_load(ft0c, ft1c, d0, d1, v0, t + 1, b, pix, B, T, hw);
+            const long nb = (long)t * B + b;
+            const long du = nb * 2 * hw + pix, dv = du + hw;
+            const long slot = (long)b * T + (T - 1 - t);
+            const long fu = slot * 2 * hw + pix, fv = fu + hw;
+            const float s0u = __fadd_rn(cur.d0u, cur.f0u), s0v = __fadd_rn(cur.d0v, cur.f0v);
+            const float s1u = __fadd_rn(cur.d1u, cur.f1u), s1v = __fadd_rn(cur.d1v, cur.f1v);
+            const WarpCoord c0 = warp_coord(x, y, clamp_pm1(s0u), clamp_pm1(s0v), g);
+            const WarpCoord c1 = warp_coord(x, y, clamp_pm1(s1u), clamp_pm1(s1v), g);
+            const Taps w0 = make_taps(c0, H, W), w1 = make_taps(c1, H, W);
+            const Frac q0 = frac_of(c0), q1 = frac_of(c1);
+            const float omt = tm.omt[t], tt = tm.t[t];
+            const float k0 = omt * cur.vis, k1 = tt * (1.f - cur.vis);
+            const float inv = 1.f / (k0 + k1);
+            const float *go = gpred + slot * C * hw + pix;
+            float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, gv = 0.f;
+            TAI_CH_LOOP(CT, C) {
+                const float gch = ld_stream(go + (long)ch * hw);
+                const TapVals a0 = sample_with_derivative(i0 + base + (long)ch * hw, w0, W, q0.ax, q0.bx, q0.ay, q0.by);
+                const TapVals a1 = sample_with_derivative(i1 + base + (long)ch * hw, w1, W, q1.ax, q1.bx, q1.ay, q1.by);
+                const float ga0 = gch * k0 * inv, ga1 = gch * k1 * inv;
+                gx0 += ga0 * a0.ddx;
+                gy0 += ga0 * a0.ddy;
+                gx1 += ga1 * a1.ddx;
+                gy1 += ga1 * a1.ddy;
+                const float o = (k0 * a0.val + k1 * a1.val) * inv;
+                gv += gch * ((omt * a0.val - tt * a1.val) - o * (omt - tt)) * inv;
+            }
+            const float r0u = (s0u >= -1.f && s0u <= 1.f) ? gx0 * sx : 0.f, r0v = (s0v >= -1.f && s0v <= 1.f) ? gy0 * sy : 0.f;
+            const float r1u = (s1u >= -1.f && s1u <= 1.f) ? gx1 * sx : 0.f, r1v = (s1v >= -1.f && s1v <= 1.f) ? gy1 * sy : 0.f;
+            gd0[du] = r0u; gd0[dv] = r0v;
+            gd1[du] = r1u; gd1[dv] = r1v;
+            gft0c[fu] = r0u; gft0c[fv] = r0v;
+            gft1c[fu] = r1u; gft1c[fv] = r1v;
+            gv0[nb * hw + pix] = gv;
+            cur = nxt;
+        }
+    }
+}
+
+static int slomo_args_ok(const char *who, int B, int T, int C, int H, int W)
+{
+    TAI_REQUIRE(B > 0 && T > 0 && C > 0 && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT,
+                "%s: bad sizes B=%d T=%d C=%d H=%d W=%d", who, B, T, C, H, W);
+    TAI_REQUIRE(T <= kSlomoMaxT, TAI_ERR_UNSUPPORTED, "%s: T=%d middle frames per launch (limit %d)", who, T, kSlomoMaxT);
+    TAI_REQUIRE(fits_int31((long long)B * T * (4 * C + 4) * H * W), TAI_ERR_TOO_LARGE, "%s: tensor has >= 2^31 elements", who);
+    return TAI_OK;
+}
+
+}  // namespace tai
+
+using namespace tai;
+
+#define TAI_SLOMO_DISPATCH(KERNEL, GRID, ST, ...)                      \
+    do {                                                               \
+        if (C == 3)                                                    \
+            KERNEL<3><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
+        else if (C == 1)                                               \
+            KERNEL<1><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
+        else                                                           \
+            KERNEL<0><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
+    } while (0)
+
+extern "C" int slomo_interp_input_forward_b200(const float *i0, const float *i1, const float *f01, const float *f10,
+                                               float *interp_input, float *f_t0_collector, float *f_t1_collector,
+                                               int B, int T, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f01 && f10 && interp_input && f_t0_collector && f_t1_collector, TAI_ERR_INVALID_ARGUMENT,
+                "slomo_interp_input_forward_b200: null pointer");
+    int rc = slomo_args_ok("slomo_interp_input_forward_b200", B, T, C, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // per (b, pixel): read 4 flows + 2C direct pixels; per t: 2C gathered pixels, write 4C + 4 (X) + 4 (collectors)
+    TimingScope ts("slomo_interp_input", st, 0.0, 4.0 * (4.0 + 2.0 * C + T * (6.0 * C + 8.0)) * B * H * W);
+    const WarpGeom g = warp_geom(H, W);
+    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const SlomoTimes tm = slomo_times(T);
+    TAI_SLOMO_DISPATCH(slomo_interp_input_kernel, grid, st, i0, i1, f01, f10, tm, interp_input, f_t0_collector,
+                       f_t1_collector, B, C, g);
+    return check_launch("slomo_interp_input_kernel");
+}
+
+extern "C" int slomo_interp_input_backward_b200(const float *i0, const float *i1, const float *f01, const float *f10,
+                                                const float *g_interp_input, const float *g_f_t0_collector,
+                                                const float *g_f_t1_collector, float *g_f01, float *g_f10,
+                                                int B, int T, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f01 && f10 && g_interp_input && g_f01 && g_f10, TAI_ERR_INVALID_ARGUMENT,
+                "slomo_interp_input_backward_b200: null pointer");
+    int rc = slomo_args_ok("slomo_interp_input_backward_b200", B, T, C, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double coll = (g_f_t0_collector ? 2.0 : 0.0) + (g_f_t1_collector ? 2.0 : 0.0);
+    TimingScope ts("slomo_interp_input_bwd", st, 0.0, 4.0 * (8.0 + T * (4.0 * C + 4.0 + coll)) * B * H * W);
+    const WarpGeom g = warp_geom(H, W);
+    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const SlomoTimes tm = slomo_times(T);
+    TAI_SLOMO_DISPATCH(slomo_interp_input_bwd_kernel, grid, st, i0, i1, f01, f10, tm, g_interp_input, g_f_t0_collector,
+                       g_f_t1_collector, g_f01, g_f10, B, C, g);
+    return check_launch("slomo_interp_input_bwd_kernel");
+}
+
+extern "C" int slomo_refine_blend_batched_forward_b200(const float *i0, const float *i1, const float *f_t0_collector,
+                                                       const float *f_t1_collector, const float *d_t0,
+                                                       const float *d_t1, const float *v_t0, float *pred,
+                                                       int B, int T, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f_t0_collector && f_t1_collector && d_t0 && d_t1 && v_t0 && pred, TAI_ERR_INVALID_ARGUMENT,
+                "slomo_refine_blend_batched_forward_b200: null pointer");
+    int rc = slomo_args_ok("slomo_refine_blend_batched_forward_b200", B, T, C, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    TimingScope ts("slomo_refine_blend_t", st, 0.0, 4.0 * (9.0 + 3.0 * C) * B * T * H * W);
+    const WarpGeom g = warp_geom(H, W);
+    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const SlomoTimes tm = slomo_times(T);
+    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_kernel, grid, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+                       pred, B, C, g);
+    return check_launch("slomo_refine_blend_t_kernel");
+}
+
+extern "C" int slomo_refine_blend_batched_backward_b200(const float *i0, const float *i1, const float *f_t0_collector,
+                                                        const float *f_t1_collector, const float *d_t0,
+                                                        const float *d_t1, const float *v_t0, const float *g_pred,
+                                                        float *g_f_t0_collector, float *g_f_t1_collector, float *g_d_t0,
+                                                        float *g_d_t1, float *g_v_t0,
+                                                        int B, int T, int C, int H, int W, void *stream)
+{
+    TAI_REQUIRE(i0 && i1 && f_t0_collector && f_t1_collector && d_t0 && d_t1 && v_t0 && g_pred && g_f_t0_collector &&
+                    g_f_t1_collector && g_d_t0 && g_d_t1 && g_v_t0,
+                TAI_ERR_INVALID_ARGUMENT, "slomo_refine_blend_batched_backward_b200: null pointer");
+    int rc = slomo_args_ok("slomo_refine_blend_batched_backward_b200", B, T, C, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    TimingScope ts("slomo_refine_blend_t_bwd", st, 0.0, 4.0 * (18.0 + 3.0 * C) * B * T * H * W);
+    const WarpGeom g = warp_geom(H, W);
+    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const SlomoTimes tm = slomo_times(T);
+    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_bwd_kernel, grid, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0,
+                       tm, g_pred, g_f_t0_collector, g_f_t1_collector, g_d_t0, g_d_t1, g_v_t0, B, C, g);
+    return check_launch("slomo_refine_blend_t_bwd_kernel");
+}

@@ -219,8 +219,11 @@ class MCNet(nn.Module):
             res_3 = self.residual3(res_m[2], res_c[2])
             res.append([res_1, res_2, res_3])
             x_hat = self.dec_cnn(h_tpl, res_1, res_2, res_3)
-            # next motion input: difference of gray frames in [0, 1]   (mcnet.py:439-447)
-            diffs.append(self._gray01(x_hat) - self._gray01(xt))
+            # next motion input: difference of gray frames in [0, 1]   (mcnet.py:439-447), one kernel on the GPU
+            if x_hat.is_cuda and self.c_dim in (1, 3):
+                diffs.append(ops.GrayDiffPairFunction.apply(x_hat.contiguous(), xt.contiguous()))
+            else:
+                diffs.append(self._gray01(x_hat) - self._gray01(xt))
             xt = x_hat
             pred.append(x_hat.view(-1, self.c_dim, image_size[0], image_size[1]))
         return pred, dyn, cont, res
@@ -243,8 +246,13 @@ class MCNetFillInModel(nn.Module):
         return {'pred': torch.stack(forward_pred, dim=1)}
 
 
-def gray_difference_frames(frames):
-    """[B,K,C,H,W] in [-1,1] -> gray frames in [0,1] -> K-1 temporal differences   (tai.py:67-68)."""
+def gray_difference_frames(frames, reverse=False):
+    """[B,K,C,H,W] in [-1,1] -> gray frames in [0,1] -> K-1 temporal differences   (tai.py:67-68); `reverse`: of the
+    time-reversed clip (tai.py:71-74).  One kernel on the GPU (bit-identical to the elementwise chain below)."""
+    if frames.is_cuda and frames.size(2) in (1, 3) and frames.size(1) > 1 and not (torch.is_grad_enabled() and frames.requires_grad):
+        return ops.gray_difference_frames(frames.contiguous(), reverse)
+    if reverse:
+        frames = torch.flip(frames, dims=[1])
     x = inverse_transform(frames)
     gray = bgr2gray_batched(x) if frames.size(2) > 1 else x
     return gray[:, 1:] - gray[:, :-1]

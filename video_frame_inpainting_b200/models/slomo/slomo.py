@@ -8,8 +8,15 @@ return tuple).  The two U-Nets stay on cuDNN; the per-time-step glue changes:
   (``flow_warp_forward_b200``) with the torch-0.3.1 sampling convention baked in (bilinear, zero padding,
   ``ix = ((g+1)/2)*(W-1)`` applied to ``g = 2*((x+u)/W - 0.5)`` -- so a zero flow samples ``x*(W-1)/W``,
   not ``x``, exactly like the reference);
-* without autograd the flow combination + first two warps (slomo.py:312-316) and the refine-clamp + two
-  warps + visibility blend (slomo.py:320-328) are one kernel each.
+* the T middle frames do not depend on each other (the U-Nets carry no state between them), so with
+  ``batch_time`` (default) the per-t loop of slomo.py:307-340 becomes ONE pass over T*B samples: one kernel writes
+  the flows of every t, both warps and the refinement network's input ``cat(I0, g0, F_t0, F_t1, g1, I1)`` in place
+  (``slomo_interp_input_*``), the refinement U-Net runs once over the T*B batch, and one kernel does
+  refine-clamp + two warps + visibility blend for every (t, b) straight into ``pred`` (``slomo_refine_blend_batched_*``).
+  Both kernels have gather-only adjoints, so the training step takes the same route;
+* the per-t formulation is kept (``batch_time = False``, or frames that require gradients): without autograd the
+  flow combination + first two warps (slomo.py:312-316) and the refine-clamp + two warps + visibility blend
+  (slomo.py:320-328) are one kernel each, with autograd the composed route through ``FlowWarper``.
 
 Quirk kept on purpose: new frames are PREPENDED (slomo.py:332-340), so ``pred[:, 0]`` is the LAST middle
 frame.
@@ -120,6 +127,7 @@ class SloMo(nn.Module):
         self.flow_warper = FlowWarper()
         self.refine_enc = Encoder(gf_dim, 4 * c_input_dim + 4)
         self.refine_dec = RefineDecoder(gf_dim, 5)
+        self.batch_time = True   # all T middle frames as one batch (same arithmetic per sample)
 
     def intermediate_flows_and_warps(self, I0, I1, F_0_1, F_1_0, t, differentiable):
         """slomo.py:312-316 -> (F_t_0, F_t_1, g_I0_F_t_0, g_I1_F_t_1); one kernel when no gradient is needed."""
@@ -149,6 +157,16 @@ class SloMo(nn.Module):
         F_0_1 = flows[:, :2].contiguous()
         F_1_0 = flows[:, 2:].contiguous()
         differentiable = torch.is_grad_enabled() and any(x.requires_grad for x in (F_0_1, I0, I1))
+        frames_need_grad = torch.is_grad_enabled() and (I0.requires_grad or I1.requires_grad)
+        if self.batch_time and I0.is_cuda and not frames_need_grad and T <= 16:
+            # one pass over the T*B samples (sample n = t*B + b); collectors and pred come out in the reference's
+            # reversed time order (slomo.py:332-340)
+            interp_input, F_t_0_collector, F_t_1_collector = ops.SlomoInterpInputFunction.apply(I0, I1, F_0_1, F_1_0, T)
+            delta_F_t_0, delta_F_t_1, V_t_0 = self.refine_dec(*self.refine_enc(interp_input))
+            pred = ops.SlomoRefineBlendFunction.apply(I0, I1, F_t_0_collector, F_t_1_collector,
+                                                      delta_F_t_0.contiguous(), delta_F_t_1.contiguous(),
+                                                      V_t_0.contiguous(), T)
+            return pred, F_0_1, F_1_0, F_t_0_collector, F_t_1_collector
         preds, ft0s, ft1s = [], [], []
         for t_ in range(T):
             t = (t_ + 1) / (T + 1)

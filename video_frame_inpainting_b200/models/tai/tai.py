@@ -65,7 +65,7 @@ class TAIFillInModel(nn.Module):
         xt = preceding_frames[:, -1]
         xt_F = following_frames[:, 0]
         diff_in = gray_difference_frames(preceding_frames)
-        diff_in_F = gray_difference_frames(torch.flip(following_frames, dims=[1]))  # time-reversed (tai.py:71-74)
+        diff_in_F = gray_difference_frames(following_frames, reverse=True)  # time-reversed (tai.py:71-74)
 
         if self.batch_streams and K == F_:
             # The two MC-Net passes share their weights and never mix samples, so they are ONE pass over the

@@ -409,6 +409,80 @@ def slomo_refine_blend(i0, i1, f_t0, f_t1, d_t0, d_t1, v_t0, t):
     return out
 
 
+class SlomoInterpInputFunction(torch.autograd.Function):
+    """slomo.py:312-318 for all T middle frames at once: ``apply(I0, I1, F_0_1, F_1_0, T)`` ->
+    (interp_input [T*B,4C+4,H,W] in sample order n = t*B + b, F_t_0_collector, F_t_1_collector [B,T,2,H,W] in the
+    reference's reversed time order).  Differentiable w.r.t. the two flows (gather-only adjoint); I0 / I1 must not
+    require gradients (they are network inputs; SloMo.forward takes the composed route otherwise)."""
+
+    @staticmethod
+    def forward(ctx, i0, i1, f01, f10, T):
+        dev = _check("slomo_interp_input", i0, i1, f01, f10)
+        B, C, H, W = i0.shape
+        assert i1.shape == i0.shape and f01.shape == f10.shape == (B, 2, H, W)
+        with torch.cuda.device(dev):
+            x = torch.empty(T * B, 4 * C + 4, H, W, device=i0.device, dtype=i0.dtype)
+            ft0c = torch.empty(B, T, 2, H, W, device=i0.device, dtype=i0.dtype)
+            ft1c = torch.empty_like(ft0c)
+            _lib.call("slomo_interp_input_forward_b200", _ptr(i0), _ptr(i1), _ptr(f01), _ptr(f10), _ptr(x), _ptr(ft0c),
+                      _ptr(ft1c), B, T, C, H, W, _stream())
+        ctx.save_for_backward(i0, i1, f01, f10)
+        ctx.T = T
+        return x, ft0c, ft1c
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gx, gft0c, gft1c):
+        i0, i1, f01, f10 = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise NotImplementedError("SlomoInterpInputFunction: no gradient w.r.t. the frames I0 / I1")
+        B, C, H, W = i0.shape
+        with torch.cuda.device(i0.device):
+            gx = gx.contiguous()
+            gft0c = gft0c.contiguous() if gft0c is not None else None
+            gft1c = gft1c.contiguous() if gft1c is not None else None
+            g01, g10 = torch.empty_like(f01), torch.empty_like(f10)
+            _lib.call("slomo_interp_input_backward_b200", _ptr(i0), _ptr(i1), _ptr(f01), _ptr(f10), _ptr(gx),
+                      _ptr(gft0c), _ptr(gft1c), _ptr(g01), _ptr(g10), B, ctx.T, C, H, W, _stream())
+        return None, None, g01, g10, None
+
+
+class SlomoRefineBlendFunction(torch.autograd.Function):
+    """slomo.py:320-328 for all T middle frames at once: ``apply(I0, I1, F_t_0_collector, F_t_1_collector, dF_t_0,
+    dF_t_1, V_t_0, T)`` -> pred [B,T,C,H,W] (reversed time order).  dF_t_*, V_t_0 in sample order n = t*B + b.
+    Differentiable w.r.t. everything but the frames."""
+
+    @staticmethod
+    def forward(ctx, i0, i1, ft0c, ft1c, d0, d1, v0, T):
+        dev = _check("slomo_refine_blend_batched", i0, i1, ft0c, ft1c, d0, d1, v0)
+        B, C, H, W = i0.shape
+        assert ft0c.shape == ft1c.shape == (B, T, 2, H, W) and d0.shape == d1.shape == (T * B, 2, H, W)
+        assert v0.shape == (T * B, 1, H, W)
+        with torch.cuda.device(dev):
+            pred = torch.empty(B, T, C, H, W, device=i0.device, dtype=i0.dtype)
+            _lib.call("slomo_refine_blend_batched_forward_b200", _ptr(i0), _ptr(i1), _ptr(ft0c), _ptr(ft1c), _ptr(d0),
+                      _ptr(d1), _ptr(v0), _ptr(pred), B, T, C, H, W, _stream())
+        ctx.save_for_backward(i0, i1, ft0c, ft1c, d0, d1, v0)
+        ctx.T = T
+        return pred
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gpred):
+        i0, i1, ft0c, ft1c, d0, d1, v0 = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise NotImplementedError("SlomoRefineBlendFunction: no gradient w.r.t. the frames I0 / I1")
+        B, C, H, W = i0.shape
+        with torch.cuda.device(i0.device):
+            gpred = gpred.contiguous()
+            gft0c, gft1c = torch.empty_like(ft0c), torch.empty_like(ft1c)
+            gd0, gd1, gv0 = torch.empty_like(d0), torch.empty_like(d1), torch.empty_like(v0)
+            _lib.call("slomo_refine_blend_batched_backward_b200", _ptr(i0), _ptr(i1), _ptr(ft0c), _ptr(ft1c), _ptr(d0),
+                      _ptr(d1), _ptr(v0), _ptr(gpred), _ptr(gft0c), _ptr(gft1c), _ptr(gd0), _ptr(gd1), _ptr(gv0),
+                      B, ctx.T, C, H, W, _stream())
+        return None, None, gft0c, gft1c, gd0, gd1, gv0, None
+
+
 # ------------------------------------------------------------------------------------------------
 # reconstruction losses (MSELoss + GDL in one pass)
 # ------------------------------------------------------------------------------------------------
@@ -531,6 +605,49 @@ def l2_normalize(v, eps=1e-12):
         out = torch.empty_like(v)
         _lib.call("l2_normalize_b200", _ptr(v), _ptr(out), v.numel(), float(eps), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# motion-stream prologue (tai.py:67-74; mcnet.py:439-447; util.py:22-41)
+# ------------------------------------------------------------------------------------------------
+
+def gray_difference_frames(frames, reverse=False):
+    """[B,K,C,H,W] in [-1,1] -> [B,K-1,1,H,W]: gray frames in [0,1], temporal differences (time-reversed input
+    order when `reverse`).  One kernel; forward only (the frames are data)."""
+    dev = _check("gray_difference_frames", frames)
+    B, K, C, H, W = frames.shape
+    with torch.cuda.device(dev):
+        out = torch.empty(B, K - 1, 1, H, W, device=dev, dtype=frames.dtype)
+        _lib.call("gray_difference_frames_b200", _ptr(frames), _ptr(out), B, K, C, H, W, int(bool(reverse)), _stream())
+    return out
+
+
+class GrayDiffPairFunction(torch.autograd.Function):
+    """``apply(a, b)`` -> gray01(a) - gray01(b) for [N,C,H,W] frames (mcnet.py:439-447), one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        dev = _check("gray_difference_pair", a, b)
+        N, C, H, W = a.shape
+        assert b.shape == a.shape
+        ctx.shape = (N, C, H, W)
+        with torch.cuda.device(dev):
+            out = torch.empty(N, 1, H, W, device=dev, dtype=a.dtype)
+            _lib.call("gray_difference_pair_forward_b200", _ptr(a), _ptr(b), _ptr(out), N, C, H, W, _stream())
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        N, C, H, W = ctx.shape
+        grad_out = grad_out.contiguous()
+        need_a, need_b = ctx.needs_input_grad
+        with torch.cuda.device(grad_out.device):
+            ga = torch.empty(N, C, H, W, device=grad_out.device, dtype=grad_out.dtype) if need_a else None
+            gb = torch.empty(N, C, H, W, device=grad_out.device, dtype=grad_out.dtype) if need_b else None
+            if need_a or need_b:
+                _lib.call("gray_difference_pair_backward_b200", _ptr(grad_out), _ptr(ga), _ptr(gb), N, C, H, W, _stream())
+        return ga, gb
 
 
 def frames_to_uint8(frames, flip_channels=None):
