@@ -258,6 +258,34 @@ int bias_act_backward_b200(const float *grad_out, const float *out, float *grad_
 int l2_normalize_b200(const float *v, float *out, int n, float eps, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gather-concatenation along batch and channel, one launch, and its adjoint.
+ * Replaces the torch.cat calls that assemble the inputs of the convolution stacks (src/models/tai/tai.py:182,195;
+ * src/models/mcnet/mcnet.py:79,91,148) and, with the T middle frames and the two MC-Net streams batched, the two
+ * copy levels (stack over t, then cat over streams) they would need.  dst [N, dst_channels, H, W] is described by
+ * blocks (at most 96 per call; the array is read on the HOST at call time):
+ *     dst[dst_sample + b*dst_sample_stride, dst_channel : dst_channel+channels] <- src[src_sample + b]   b < samples
+ * src == NULL fills the slot with fill_value.  A source may be a channel slice of a larger tensor (src points at
+ * its first element, src_sample_stride is the parent's sample pitch).  channels*H*W must be a multiple of 4 and all pointers 16-byte
+ * aligned (TAI_ERR_UNSUPPORTED otherwise).  The blocks must not overlap in dst; dst elements no block covers are
+ * left untouched.  Backward: the same blocks with `src` pointing at the GRADIENT buffers of the sources, which are
+ * overwritten from grad_dst (a source sample belongs to one block, so nothing needs zero-filling or atomics). */
+typedef struct tai_cat_block {
+    const float *src;
+    long long src_sample;
+    long long src_sample_stride; /* floats between source samples; 0 = dense (channels*H*W); larger for a channel slice */
+    long long dst_sample;
+    long long dst_sample_stride;
+    long long dst_channel;
+    int channels;
+    int samples;
+    float fill_value;
+} tai_cat_block;
+int gather_concat_forward_b200(const tai_cat_block *blocks, int nblocks, float *dst, long long dst_channels,
+                               int H, int W, void *stream);
+int gather_concat_backward_b200(const tai_cat_block *blocks, int nblocks, const float *grad_dst, long long dst_channels,
+                                int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Motion-stream prologue.  Replaces the elementwise chains of
  * src/models/tai/tai.py:67-74 (inverse_transform -> bgr2gray_batched -> frame differences, and the same on the
  * time-reversed following frames), src/models/mcnet/mcnet.py:439-447 (the next motion input inside the

@@ -245,6 +245,45 @@ def test_motion_prologue_kernels_bit_exact(cuda, C):
     assert O.rel_err(ga.cpu().numpy(), ga_ref.cpu().numpy()) < 1e-6 and O.rel_err(gb.cpu().numpy(), gb_ref.cpu().numpy()) < 1e-6
 
 
+def test_gather_concat_matches_torch_cat(cuda):
+    """gather_concat_* (tai.py:182,195; mcnet.py:79,91,148): bit-identical to torch.cat / slicing / stacking,
+    including a channel-slice source, a constant plane, a strided destination, and the adjoint."""
+    import torch
+    from video_frame_inpainting_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, T, C, H, W = 3, 4, 5, 6, 8
+    xs = [torch.randn(2 * B, C, H, W, generator=g).cuda().requires_grad_(True) for _ in range(T)]
+    # (forward stream at t | backward stream at T-1-t), the merge of TAIFillInModel._forward_batched
+    blocks = []
+    for t in range(T):
+        blocks += [(t, 0, B, t * B, 1, 0, C, 0.0), (T - 1 - t, B, B, t * B, 1, C, C, 0.0)]
+    got = ops.GatherConcatFunction.apply((T * B, 2 * C, tuple(blocks)), *xs)
+    ref = torch.cat([torch.cat([xs[t][:B] for t in range(T)], 0), torch.cat([xs[T - 1 - t][B:] for t in range(T)], 0)], 1)
+    assert torch.equal(got, ref)
+    w = torch.randn(ref.shape, generator=g).cuda()
+    g_got = torch.autograd.grad((got * w).sum(), xs)
+    g_ref = torch.autograd.grad((ref * w).sum(), xs)
+    assert all(torch.equal(a, b) for a, b in zip(g_got, g_ref))
+    # plain channel cat with a channel-slice view as one source, then a constant plane per sample block
+    state = torch.randn(B, 2 * C, H, W, generator=g).cuda().requires_grad_(True)
+    a = torch.randn(B, 3, H, W, generator=g).cuda().requires_grad_(True)
+    hview = state[:, C:]
+    got = ops.cat_channels((a, hview))
+    ref = torch.cat((a, hview), 1)
+    assert torch.equal(got, ref)
+    gg = torch.autograd.grad((got * got).sum(), (a, state))
+    gr = torch.autograd.grad((ref * ref).sum(), (a, state))
+    assert torch.equal(gg[0], gr[0]) and torch.equal(gg[1], gr[1])
+    blocks = [(0, 0, B, 0, 1, 0, 3, 0.0), (None, 0, 2, 0, 1, 3, 1, 0.25), (None, 0, 1, 2, 1, 3, 1, 0.75)]
+    got = ops.GatherConcatFunction.apply((B, 4, tuple(blocks)), a)
+    plane = torch.cat([a.new_full((2, 1, H, W), 0.25), a.new_full((1, 1, H, W), 0.75)], 0)
+    assert torch.equal(got, torch.cat((a, plane), 1))
+    # stack along dim 1 through a strided destination: out[b, t] = xs[t][b]
+    blocks = [(t, 0, 2 * B, t, T, 0, C, 0.0) for t in range(T)]
+    got = ops.GatherConcatFunction.apply((2 * B * T, C, tuple(blocks)), *xs).view(2 * B, T, C, H, W)
+    assert torch.equal(got, torch.stack(xs, 1))
+
+
 def test_frames_to_uint8_and_png_layout(cuda, tmp_path):
     """Device-side float -> 8-bit conversion, byte-exact against PNGs written by the reference's own
     save_video_frames (tests/golden/frames_u8_ref.npz), and the predict.py file layout."""

@@ -54,12 +54,22 @@ SIGNATURES = {
     "bias_act_backward_workspace_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _c_i]),
     "bias_act_backward_b200": (_c_i, [_c_f] * 5 + [ctypes.c_longlong] + [_c_i] * 3 + [ctypes.c_float, _c_s]),
     "l2_normalize_b200": (_c_i, [_c_f] * 2 + [_c_i, ctypes.c_float, _c_s]),
+    "gather_concat_forward_b200": (_c_i, [ctypes.c_void_p, _c_i, _c_f, ctypes.c_longlong, _c_i, _c_i, _c_s]),
+    "gather_concat_backward_b200": (_c_i, [ctypes.c_void_p, _c_i, _c_f, ctypes.c_longlong, _c_i, _c_i, _c_s]),
     "gray_difference_frames_b200": (_c_i, [_c_f] * 2 + [_c_i] * 6 + [_c_s]),
     "gray_difference_pair_forward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 3 + [_c_s]),
     "gray_difference_pair_backward_b200": (_c_i, [_c_f] * 3 + [ctypes.c_longlong] + [_c_i] * 3 + [_c_s]),
     "frames_to_uint8_b200": (_c_i, [_c_f] * 2 + [ctypes.c_longlong] + [_c_i] * 4 + [_c_s]),
     "tai_b200_ffma_probe": (_c_i, [_c_f] + [_c_i] * 4 + [_c_s]),
 }
+
+class CatBlock(ctypes.Structure):
+    """tai_cat_block of include/tai_b200.h."""
+    _fields_ = [("src", ctypes.c_void_p), ("src_sample", ctypes.c_longlong), ("src_sample_stride", ctypes.c_longlong),
+                ("dst_sample", ctypes.c_longlong),
+                ("dst_sample_stride", ctypes.c_longlong), ("dst_channel", ctypes.c_longlong), ("channels", ctypes.c_int),
+                ("samples", ctypes.c_int), ("fill_value", ctypes.c_float)]
+
 
 ERROR_NAMES = {0: "TAI_OK", -1: "TAI_ERR_INVALID_ARGUMENT", -2: "TAI_ERR_UNSUPPORTED",
                -3: "TAI_ERR_TOO_LARGE", -4: "TAI_ERR_CUDA"}

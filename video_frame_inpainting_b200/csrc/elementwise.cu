@@ -7,26 +7,6 @@
 namespace tai {
 
 
-// Grid for a grid-stride kernel whose loop handles `unroll` items per trip: every thread makes the same number
-// of trips (a multiple of `unroll`), and the grid fits the kernel's real residency (occupancy query, cached by
-// the caller) so that it runs as ONE wave.  Small CTAs keep the per-SM CTA count even (1024 CTAs on 148 SMs:
-// 7 vs 6.9 average; 512 larger CTAs: 4 vs 3.5).
-template <typename K>
-static inline unsigned stream_grid_occ(K kernel, long work_items, int block, int unroll)
-{
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const long cap = (long)sm_count() * per_sm;
-    long g = (work_items + block - 1) / block;
-    if (g > cap) {
-        long trips = (g + cap - 1) / cap;
-        trips = (trips + unroll - 1) / unroll * unroll;
-        g = (g + trips - 1) / trips;
-    }
-    if (g < 1) g = 1;
-    return (unsigned)g;
-}
-
 // ------------------------------------------------------------------------------------------------
 // ConvLSTM gates (mcnet.py:287-293).  conv_out [B,4F,HW] holds (i,j,f,o) as four contiguous F*HW
 // slabs per sample; state [B,2F,HW] holds (c,h).  28 B of traffic per state element.
@@ -321,7 +301,7 @@ slomo_refine_blend_kernel(const float *__restrict__ i0, const float *__restrict_
         const float vis0 = ld_stream(v0 + (long)b * hw + pix);
         const float vis1 = 1.f - vis0;
         const float k0 = omt * vis0, k1 = t * vis1;
-        const float norm = k0 + k1;
+        const float inv = 1.f / (k0 + k1);   // one IEEE reciprocal for the C channels (the reference divides each: <= 1 ulp apart)
         const long base = (long)b * C * hw;
         if (CT) {
             float a0[CT ? CT : 1], a1[CT ? CT : 1];
@@ -329,11 +309,11 @@ slomo_refine_blend_kernel(const float *__restrict__ i0, const float *__restrict_
                 a0[ch] = sample(i0 + base + (long)ch * hw, w0, W);
                 a1[ch] = sample(i1 + base + (long)ch * hw, w1, W);
             }
-            TAI_CH_LOOP(CT, C) out[base + (long)ch * hw + pix] = (k0 * a0[ch] + k1 * a1[ch]) / norm;
+            TAI_CH_LOOP(CT, C) out[base + (long)ch * hw + pix] = (k0 * a0[ch] + k1 * a1[ch]) * inv;
         } else {
             for (int ch = 0; ch < C; ++ch) {
                 const float a0 = sample(i0 + base + (long)ch * hw, w0, W), a1 = sample(i1 + base + (long)ch * hw, w1, W);
-                out[base + (long)ch * hw + pix] = (k0 * a0 + k1 * a1) / norm;
+                out[base + (long)ch * hw + pix] = (k0 * a0 + k1 * a1) * inv;
             }
         }
     }

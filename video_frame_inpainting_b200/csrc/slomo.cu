@@ -255,7 +255,7 @@ __device__ __forceinline__ RefineIn refine_load(const float *__restrict__ ft0c, 
 }
 
 template <int CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 slomo_refine_blend_t_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
                             const float *__restrict__ ft0c, const float *__restrict__ ft1c,
                             const float *__restrict__ d0, const float *__restrict__ d1, const float *__restrict__ v0,
@@ -278,7 +278,7 @@ slomo_refine_blend_t_kernel(const float *__restrict__ i0, const float *__restric
             const Taps w1 = make_taps(warp_coord(x, y, r1u, r1v, g), H, W);
             const float vis1 = 1.f - cur.vis;
             const float k0 = tm.omt[t] * cur.vis, k1 = tm.t[t] * vis1;
-            const float norm = k0 + k1;
+            const float inv = 1.f / (k0 + k1);   // one IEEE reciprocal for the C channels (the reference divides each)
             float *out = pred + ((long)b * T + (T - 1 - t)) * C * hw + pix;   // reversed time order (slomo.py:332-340)
             if (CT) {
                 float a0[CT ? CT : 1], a1[CT ? CT : 1];
@@ -286,11 +286,11 @@ slomo_refine_blend_t_kernel(const float *__restrict__ i0, const float *__restric
                     a0[ch] = sample(i0 + base + (long)ch * hw, w0, W);
                     a1[ch] = sample(i1 + base + (long)ch * hw, w1, W);
                 }
-                TAI_CH_LOOP(CT, C) out[(long)ch * hw] = (k0 * a0[ch] + k1 * a1[ch]) / norm;
+                TAI_CH_LOOP(CT, C) out[(long)ch * hw] = (k0 * a0[ch] + k1 * a1[ch]) * inv;
             } else {
                 for (int ch = 0; ch < C; ++ch) {
                     const float a0 = sample(i0 + base + (long)ch * hw, w0, W), a1 = sample(i1 + base + (long)ch * hw, w1, W);
-                    out[(long)ch * hw] = (k0 * a0 + k1 * a1) / norm;
+                    out[(long)ch * hw] = (k0 * a0 + k1 * a1) * inv;
                 }
             }
             cur = nxt;
@@ -375,14 +375,15 @@ static int slomo_args_ok(const char *who, int B, int T, int C, int H, int W)
 
 using namespace tai;
 
-#define TAI_SLOMO_DISPATCH(KERNEL, GRID, ST, ...)                      \
-    do {                                                               \
-        if (C == 3)                                                    \
-            KERNEL<3><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
-        else if (C == 1)                                               \
-            KERNEL<1><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
-        else                                                           \
-            KERNEL<0><<<GRID, 256, 0, ST>>>(__VA_ARGS__);              \
+// grid = one balanced wave of the kernel's real residency (equal grid-stride trips per thread)
+#define TAI_SLOMO_DISPATCH(KERNEL, ITEMS, ST, ...)                                                    \
+    do {                                                                                              \
+        if (C == 3)                                                                                   \
+            KERNEL<3><<<stream_grid_occ(KERNEL<3>, ITEMS, 256, 1), 256, 0, ST>>>(__VA_ARGS__);        \
+        else if (C == 1)                                                                              \
+            KERNEL<1><<<stream_grid_occ(KERNEL<1>, ITEMS, 256, 1), 256, 0, ST>>>(__VA_ARGS__);        \
+        else                                                                                          \
+            KERNEL<0><<<stream_grid_occ(KERNEL<0>, ITEMS, 256, 1), 256, 0, ST>>>(__VA_ARGS__);        \
     } while (0)
 
 extern "C" int slomo_interp_input_forward_b200(const float *i0, const float *i1, const float *f01, const float *f10,
@@ -397,9 +398,9 @@ extern "C" int slomo_interp_input_forward_b200(const float *i0, const float *i1,
     // per (b, pixel): read 4 flows + 2C direct pixels; per t: 2C gathered pixels, write 4C + 4 (X) + 4 (collectors)
     TimingScope ts("slomo_interp_input", st, 0.0, 4.0 * (4.0 + 2.0 * C + T * (6.0 * C + 8.0)) * B * H * W);
     const WarpGeom g = warp_geom(H, W);
-    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    TAI_SLOMO_DISPATCH(slomo_interp_input_kernel, grid, st, i0, i1, f01, f10, tm, interp_input, f_t0_collector,
+    TAI_SLOMO_DISPATCH(slomo_interp_input_kernel, items, st, i0, i1, f01, f10, tm, interp_input, f_t0_collector,
                        f_t1_collector, B, C, g);
     return check_launch("slomo_interp_input_kernel");
 }
@@ -417,9 +418,9 @@ extern "C" int slomo_interp_input_backward_b200(const float *i0, const float *i1
     const double coll = (g_f_t0_collector ? 2.0 : 0.0) + (g_f_t1_collector ? 2.0 : 0.0);
     TimingScope ts("slomo_interp_input_bwd", st, 0.0, 4.0 * (8.0 + T * (4.0 * C + 4.0 + coll)) * B * H * W);
     const WarpGeom g = warp_geom(H, W);
-    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    TAI_SLOMO_DISPATCH(slomo_interp_input_bwd_kernel, grid, st, i0, i1, f01, f10, tm, g_interp_input, g_f_t0_collector,
+    TAI_SLOMO_DISPATCH(slomo_interp_input_bwd_kernel, items, st, i0, i1, f01, f10, tm, g_interp_input, g_f_t0_collector,
                        g_f_t1_collector, g_f01, g_f10, B, C, g);
     return check_launch("slomo_interp_input_bwd_kernel");
 }
@@ -436,9 +437,9 @@ extern "C" int slomo_refine_blend_batched_forward_b200(const float *i0, const fl
     cudaStream_t st = (cudaStream_t)stream;
     TimingScope ts("slomo_refine_blend_t", st, 0.0, 4.0 * (9.0 + 3.0 * C) * B * T * H * W);
     const WarpGeom g = warp_geom(H, W);
-    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_kernel, grid, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_kernel, items, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                        pred, B, C, g);
     return check_launch("slomo_refine_blend_t_kernel");
 }
@@ -458,9 +459,9 @@ extern "C" int slomo_refine_blend_batched_backward_b200(const float *i0, const f
     cudaStream_t st = (cudaStream_t)stream;
     TimingScope ts("slomo_refine_blend_t_bwd", st, 0.0, 4.0 * (18.0 + 3.0 * C) * B * T * H * W);
     const WarpGeom g = warp_geom(H, W);
-    const unsigned grid = stream_grid((long)B * H * W, 256);
+    const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_bwd_kernel, grid, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0,
+    TAI_SLOMO_DISPATCH(slomo_refine_blend_t_bwd_kernel, items, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0,
                        tm, g_pred, g_f_t0_collector, g_f_t1_collector, g_d_t0, g_d_t1, g_v_t0, B, C, g);
     return check_launch("slomo_refine_blend_t_bwd_kernel");
 }

@@ -19,6 +19,26 @@ static inline unsigned stream_grid(long work_items, int block)
     return (unsigned)g;
 }
 
+// Grid for a grid-stride kernel whose loop handles `unroll` items per trip: every thread makes the same number
+// of trips (a multiple of `unroll`), and the grid fits the kernel's real residency (occupancy query, cached by
+// the caller) so that it runs as ONE wave.  Small CTAs keep the per-SM CTA count even (1024 CTAs on 148 SMs:
+// 7 vs 6.9 average; 512 larger CTAs: 4 vs 3.5).
+template <typename K>
+static inline unsigned stream_grid_occ(K kernel, long work_items, int block, int unroll)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long cap = (long)sm_count() * per_sm;
+    long g = (work_items + block - 1) / block;
+    if (g > cap) {
+        long trips = (g + cap - 1) / cap;
+        trips = (trips + unroll - 1) / unroll * unroll;
+        g = (g + trips - 1) / trips;
+    }
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bilinear backward warp (slomo.py:265-286 + torch-0.3.1 grid_sample: bilinear, zero padding).
 // The coordinate chain is evaluated with one IEEE rounding per reference operation (no FMA

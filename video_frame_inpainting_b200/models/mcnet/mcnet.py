@@ -68,6 +68,14 @@ class ContentEnc(nn.Module):
         return self.pool3(x), skips
 
 
+def _cat_channels(a, b):
+    """torch.cat((a, b), dim=1) -- through the library's gather kernel on the GPU (one launch each way; the adjoint
+    writes two contiguous gradients instead of returning strided slices)."""
+    if ops.gather_concat_ok(a, b):
+        return ops.cat_channels((a, b))
+    return torch.cat((a, b), dim=1)
+
+
 class CombLayers(nn.Module):
     """cat(h_dyn, h_cont) -> three 3x3 convolutions   (mcnet.py:122-153)."""
 
@@ -76,7 +84,7 @@ class CombLayers(nn.Module):
         self.h_comb = FusedSequential(*_conv_relu_chain([gf_dim * 8, gf_dim * 4, gf_dim * 2, gf_dim * 4], 3))
 
     def forward(self, h_dyn, h_cont):
-        return self.h_comb(torch.cat((h_dyn, h_cont), dim=1))
+        return self.h_comb(_cat_channels(h_dyn, h_cont))
 
 
 class Residual(nn.Module):
@@ -88,7 +96,7 @@ class Residual(nn.Module):
                                  nn.Conv2d(out_dim, out_dim, 3, padding=1))
 
     def forward(self, input_dyn, input_cont):
-        return self.res(torch.cat((input_dyn, input_cont), dim=1))
+        return self.res(_cat_channels(input_dyn, input_cont))
 
 
 class DecCnn(nn.Module):

@@ -67,15 +67,19 @@ class TAIFillInModel(nn.Module):
         diff_in = gray_difference_frames(preceding_frames)
         diff_in_F = gray_difference_frames(following_frames, reverse=True)  # time-reversed (tai.py:71-74)
 
+        weights = self.blend_weights(T)
+        B = xt.size(0)
         if self.batch_streams and K == F_:
             # The two MC-Net passes share their weights and never mix samples, so they are ONE pass over the
             # 2B clips [preceding; time-reversed following] (the reference runs them back to back,
             # tai.py:77-84): half the launches, and at small batches twice the tiles per kernel (batch-1
-            # inference ran 39 ms of kernels of <= 64 tiles on 148 SMs).  unbind() hands each stream its half
-            # as a contiguous view; its backward is a single stack.
-            B = xt.size(0)
+            # inference ran 39 ms of kernels of <= 64 tiles on 148 SMs).
             both = self.generator(K, T, torch.cat([diff_in, diff_in_F], 0), torch.cat([xt, xt_F], 0))
+            if self.batch_time and T > 1 and len(set((w[0], w[1]) for w in weights)) == 1 and \
+                    ops.gather_concat_ok(*both[0], *both[1], *both[2], *[r for res_t in both[3] for r in res_t]):
+                return self._forward_batched(T, B, both, weights)
 
+            # unbind() hands each stream its half as a contiguous view; its backward is a single stack
             def halves(x):
                 return x.view(2, B, *x.shape[1:]).unbind(0)
 
@@ -93,14 +97,12 @@ class TAIFillInModel(nn.Module):
         backward_pred, backward_dyn = backward_pred[::-1], backward_dyn[::-1]
         backward_cont, backward_res = backward_cont[::-1], backward_res[::-1]
 
-        weights = self.blend_weights(T)
         combination, outputs_1, outputs_2 = [], [], []
         if self.batch_time and T > 1:
             # The T kernel-net evaluations depend on MC-Net outputs only, not on each other (tai.py:91-105 runs
             # them in a loop): ONE pass over the T*B samples [t = 0; t = 1; ...], the time ratio as a per-block
             # constant plane, then the fused pad + sepconv + blend kernel over all T*B frames (per t when the
             # blend weights differ, bi-TWI).
-            B = xt.size(0)
 
             def cat(xs):
                 return torch.cat(list(xs), 0)
@@ -144,6 +146,58 @@ class TAIFillInModel(nn.Module):
         }
 
 
+    def _forward_batched(self, T, B, both, weights):
+        """Both MC-Net streams as one 2B batch AND the kernel network once over the T*B middle frames: every input
+        of the kernel network is gathered straight from the per-step tensors of the 2B pass -- sample (t, b) takes
+        the forward stream of step t (samples 0..B-1) and the backward stream of step T-1-t (samples B..2B-1), the
+        time reversal of tai.py:85-88 -- in ONE launch per tensor (``gather_concat_*``), where stacking the T steps
+        of each stream and then concatenating the streams along channels would copy everything twice."""
+        pred_l, dyn_l, cont_l, res_l = both
+
+        def merge(xs):   # T x [2B,C,h,w] -> [T*B, 2C, h, w]: (forward stream at t | backward stream at T-1-t)
+            C = xs[0].shape[1]
+            blocks = []
+            for t in range(T):
+                blocks.append((t, 0, B, t * B, 1, 0, C, 0.0))
+                blocks.append((T - 1 - t, B, B, t * B, 1, C, C, 0.0))
+            return ops.GatherConcatFunction.apply((T * B, 2 * C, tuple(blocks)), *xs)
+
+        merged_res = [self.merge_residual1.res(merge([r[0] for r in res_l])),
+                      self.merge_residual2.res(merge([r[1] for r in res_l])),
+                      self.merge_residual3.res(merge([r[2] for r in res_l]))]
+        # kernel-network input: cat(dyn1, dyn2, cont1, cont2) of tai.py:188
+        Cd, Cc = dyn_l[0].shape[1], cont_l[0].shape[1]
+        blocks = []
+        for t in range(T):
+            blocks += [(t, 0, B, t * B, 1, 0, Cd, 0.0), (T - 1 - t, B, B, t * B, 1, Cd, Cd, 0.0),
+                       (T + t, 0, B, t * B, 1, 2 * Cd, Cc, 0.0), (2 * T - 1 - t, B, B, t * B, 1, 2 * Cd + Cc, Cc, 0.0)]
+        x0 = ops.GatherConcatFunction.apply((T * B, 2 * Cd + 2 * Cc, tuple(blocks)), *dyn_l, *cont_l)
+        v1, h1, v2, h2 = self.kernelnet.kernel_maps_from(x0, merged_res, ratio=[w[2] for w in weights])
+        # the two predictions per middle frame, [pf; pb] as one tensor of 2*T*B samples
+        C = pred_l[0].shape[1]
+        blocks = []
+        for t in range(T):
+            blocks += [(t, 0, B, t * B, 1, 0, C, 0.0), (T - 1 - t, B, B, (T + t) * B, 1, 0, C, 0.0)]
+        pfb = ops.GatherConcatFunction.apply((2 * T * B, C, tuple(blocks)), *pred_l)
+        pred, dot1, dot2 = self.kernelnet.apply_maps(pfb[:T * B], pfb[T * B:], v1, h1, v2, h2, weights[0][0], weights[0][1])
+        # outputs [B,T,C,H,W]: pred_forward[b,t] = stream 0 of step t, pred_backward[b,t] = stream 1 of step T-1-t
+        blocks = []
+        for t in range(T):
+            blocks += [(t, 0, B, t, T, 0, C, 0.0), (T - 1 - t, B, B, B * T + t, T, 0, C, 0.0)]
+        fb = ops.GatherConcatFunction.apply((2 * B * T, C, tuple(blocks)), *pred_l)
+        HW = pred.shape[2:]
+
+        def bt(x):    # [T*B,C,H,W] (t-major) -> [B,T,C,H,W]
+            return x.view(T, B, C, *HW).transpose(0, 1).contiguous()
+        return {
+            'pred': bt(pred),
+            'pred_forward': fb[:B * T].view(B, T, C, *HW),
+            'pred_backward': fb[B * T:].view(B, T, C, *HW),
+            'interp_net_outputs_1': bt(dot1),
+            'interp_net_outputs_2': bt(dot2),
+        }
+
+
 class TAI(nn.Module):
     """Kernel network: encoder / decoder over [dyn1, dyn2, cont1, cont2] -> four 1-D kernel maps
     V1, H1, V2, H2 [B, ks, H, W], applied to the two predictions   (tai.py:123-237)."""
@@ -178,8 +232,12 @@ class TAI(nn.Module):
 
     def kernel_maps(self, variableDyn1, variableDyn2, variableCont1, variableCont2, variableRes, ratio=0):
         """Everything of tai.py:188-226,230-235 that produces V1, H1, V2, H2."""
-        nb = self.num_block
         x = torch.cat([variableDyn1, variableDyn2, variableCont1, variableCont2], 1)
+        return self.kernel_maps_from(x, variableRes, ratio)
+
+    def kernel_maps_from(self, x, variableRes, ratio=0):
+        """kernel_maps for an already assembled input cat(dyn1, dyn2, cont1, cont2)."""
+        nb = self.num_block
         enc = []
         for i in range(nb - 3):
             enc.append(self.moduleConv[i](x))
@@ -187,12 +245,17 @@ class TAI(nn.Module):
         for i in range(nb - 1):
             x = self.moduleDeconv[i](x)
             if i == self.rc_loc - 1:  # time-ratio plane; reachable only when num_block >= 5 (tai.py:213-217)
-                if isinstance(ratio, (list, tuple)):  # batch = len(ratio) equal blocks, one ratio per block
-                    n = x.size(0) // len(ratio)
-                    plane = torch.cat([x.new_full((n, 1, x.size(2), x.size(3)), float(r)) for r in ratio], 0)
+                ratios = list(ratio) if isinstance(ratio, (list, tuple)) else [ratio]
+                n = x.size(0) // len(ratios)      # batch = len(ratios) equal blocks, one ratio per block
+                if x.is_cuda and (x.size(2) * x.size(3)) % 4 == 0:
+                    # x and the constant plane(s) in one launch (fill blocks), one launch for the adjoint
+                    Cx = x.size(1)
+                    blocks = [(0, 0, x.size(0), 0, 1, 0, Cx, 0.0)]
+                    blocks += [(None, 0, n, i * n, 1, Cx, 1, float(r)) for i, r in enumerate(ratios)]
+                    x = ops.GatherConcatFunction.apply((x.size(0), Cx + 1, tuple(blocks)), x.contiguous())
                 else:
-                    plane = x.new_full((x.size(0), 1, x.size(2), x.size(3)), float(ratio))
-                x = torch.cat([x, plane], dim=1)
+                    plane = torch.cat([x.new_full((n, 1, x.size(2), x.size(3)), float(r)) for r in ratios], 0)
+                    x = torch.cat([x, plane], dim=1)
             x = self.moduleUpsample[i](x)
             x = x + (enc[nb - 3 - i - 1] if i < nb - 3 else variableRes[nb - i - 1])
         return (self.moduleVertical1(x), self.moduleHorizontal1(x), self.moduleVertical2(x), self.moduleHorizontal2(x))

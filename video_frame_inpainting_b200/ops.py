@@ -6,6 +6,8 @@ operator (src/separable_convolution/SeparableConvolution.py:48-49,86-87) -- ther
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -605,6 +607,84 @@ def l2_normalize(v, eps=1e-12):
         out = torch.empty_like(v)
         _lib.call("l2_normalize_b200", _ptr(v), _ptr(out), v.numel(), float(eps), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# gather-concatenation (tai.py:182,195; mcnet.py:79,91,148; the stack-then-cat of the batched kernel network)
+# ------------------------------------------------------------------------------------------------
+
+class GatherConcatFunction(torch.autograd.Function):
+    """``apply(spec, *tensors)`` -> dst [N, Ctot, H, W].  ``spec = (N, Ctot, blocks)``; a block is
+    ``(tensor_index or None, src_sample, samples, dst_sample, dst_sample_stride, dst_channel, channels, fill)``:
+    dst[dst_sample + b*stride, dst_channel : dst_channel+channels] <- tensors[i][src_sample + b] (or the constant
+    ``fill`` when the index is None).  The blocks must tile dst completely and use every sample of every tensor
+    exactly once (checked): the adjoint then overwrites each source gradient in the same single launch."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        N, Ctot, blocks = spec
+        dev = tensors[0].device
+        assert gather_concat_ok(*tensors), "gather_concat: float32 CUDA NCHW tensors, C*H*W a multiple of 4"
+        H, W = tensors[0].shape[-2:]
+        covered = [0] * len(tensors)
+        dst_elems = 0
+        arr = (_lib.CatBlock * len(blocks))()
+        for k, (ti, ss, n, ds, dstride, dc, ch, fill) in enumerate(blocks):
+            if ti is not None:
+                t = tensors[ti]
+                assert t.shape[1] == ch and tuple(t.shape[-2:]) == (H, W) and ss + n <= t.shape[0]
+                covered[ti] += n
+            arr[k] = _lib.CatBlock(_ptr(tensors[ti]) if ti is not None else None, ss,
+                                   tensors[ti].stride(0) if ti is not None else 0, ds, dstride, dc, ch, n, float(fill))
+            dst_elems += n * ch
+        assert dst_elems == N * Ctot, "gather_concat: the blocks do not tile the destination"
+        assert all(c == t.shape[0] for c, t in zip(covered, tensors)), "gather_concat: a source sample is unused or used twice"
+        with torch.cuda.device(dev):
+            dst = torch.empty(N, Ctot, H, W, device=dev, dtype=tensors[0].dtype)
+            _lib.call("gather_concat_forward_b200", ctypes.addressof(arr), len(blocks), _ptr(dst), Ctot, H, W, _stream())
+        ctx.spec = spec
+        ctx.shapes = [tuple(t.shape) for t in tensors]
+        return dst
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gdst):
+        N, Ctot, blocks = ctx.spec
+        gdst = gdst.contiguous()
+        H, W = gdst.shape[-2:]
+        with torch.cuda.device(gdst.device):
+            grads = [torch.empty(sh, device=gdst.device, dtype=gdst.dtype) if need else None
+                     for sh, need in zip(ctx.shapes, ctx.needs_input_grad[1:])]
+            live = [b for b in blocks if b[0] is not None and grads[b[0]] is not None]
+            if live:
+                arr = (_lib.CatBlock * len(live))()
+                for k, (ti, ss, n, ds, dstride, dc, ch, fill) in enumerate(live):
+                    arr[k] = _lib.CatBlock(_ptr(grads[ti]), ss, 0, ds, dstride, dc, ch, n, 0.0)
+                _lib.call("gather_concat_backward_b200", ctypes.addressof(arr), len(live), _ptr(gdst), Ctot, H, W, _stream())
+        return (None,) + tuple(grads)
+
+
+def cat_channels(tensors):
+    """torch.cat(tensors, dim=1) for contiguous NCHW CUDA tensors through the gather kernel (one launch each way)."""
+    N = tensors[0].shape[0]
+    blocks, c0 = [], 0
+    for i, t in enumerate(tensors):
+        blocks.append((i, 0, N, 0, 1, c0, t.shape[1], 0.0))
+        c0 += t.shape[1]
+    return GatherConcatFunction.apply((N, c0, tuple(blocks)), *tensors)
+
+
+def gather_concat_ok(*tensors):
+    """The gather kernel moves 16-byte vectors out of NCHW tensors whose samples are dense (channel slices of a
+    larger tensor are fine: only the sample pitch differs): every sample run (C*H*W floats), every sample pitch and
+    every base address must be a multiple of 16 bytes."""
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4):
+            return False
+        C, H, W = t.shape[1:]
+        if (C * H * W) % 4 or t.stride()[1:] != (H * W, W, 1) or t.stride(0) % 4 or t.stride(0) < C * H * W or t.data_ptr() % 16:
+            return False
+    return True
 
 
 # ------------------------------------------------------------------------------------------------
