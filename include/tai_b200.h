@@ -72,6 +72,12 @@ int SeparableConvolution_cuda_forward_b200(const float *input, const float *vert
  *
  *   grad_output [B,C,Ho,Wo] -> grad_input [B,C,Hi,Wi], grad_vertical / grad_horizontal [B,ks,Ho,Wo].
  *   Any of the three gradient pointers may be NULL to skip that gradient.
+ *   Determinism: grad_vertical / grad_horizontal are bit-reproducible.  grad_input is accumulated with FP32
+ *   red.global from overlapping source tiles (the callee zeroes it on `stream` first), so its summation order -- and
+ *   with it the last bits -- can differ from run to run, where the reference's gather kernel (kernel.cu:120-162) is
+ *   deterministic; the difference stays inside the 1e-4 parity bound, and integer-valued inputs (the tap-count test)
+ *   are exact in any order.  The same holds for g_img of flow_warp_backward_b200 and for the fused
+ *   tai_fused_backward_b200 (g_pred_f / g_pred_b).
  */
 int SeparableConvolution_cuda_backward_b200(const float *grad_output, const float *input,
                                             const float *vertical, const float *horizontal,
@@ -139,7 +145,9 @@ int convlstm_gates_backward_b200(const float *conv_out, const float *state, cons
  */
 int flow_warp_forward_b200(const float *img, const float *uv, float *out,
                            int B, int C, int H, int W, void *stream);
-/* g_img is accumulated with atomics and is zeroed by the callee on `stream` first. */
+/* g_img is accumulated with FP32 atomics and is zeroed by the callee on `stream` first: its last bits are not
+ * reproducible from run to run (g_uv is).  The models never ask for g_img (the frames are network inputs); the
+ * Super SloMo stages below have gather-only, deterministic adjoints. */
 int flow_warp_backward_b200(const float *img, const float *uv, const float *grad_out,
                             float *g_img, float *g_uv, int B, int C, int H, int W, void *stream);
 

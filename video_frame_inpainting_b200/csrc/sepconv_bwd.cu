@@ -7,11 +7,8 @@
 // The reference launches three kernels that each re-walk the ks x ks window (kernel.cu:200-239).
 // Here gV and gH come out of ONE pass over the window (the same LDS of I feeds both), with the
 // lane layout of the forward kernel; gI is a separate gather kernel.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "sepconv_bwd_vh_v3.cuh"
-#include "sepconv_bwd_i_v3.cuh"
 #include "sepconv_bwd_i_v4.cuh"
 
 namespace tai {
@@ -502,43 +499,7 @@ static int launch_vh(const BwdParams &p, cudaStream_t st)
     return TAI_ERR_UNSUPPORTED;
 }
 
-// Persistent TMA-fed scatter kernel for gI (sepconv_bwd_i_v3.cuh); +1 = not TMA-describable, fall back.
-template <int KS>
-static int launch_gi_v3(const BwdParams &p0, cudaStream_t st)
-{
-    using Cfg = GiV3Cfg<KS>;
-    BwdParams p = p0;
-    GiV3Maps maps;
-    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
-        !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
-        return 1;
-    p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
-    p.nty = ceil_div(p.Ho, Cfg::TILE_H);
-    auto kern = sepconv_bwd_i_v3_kernel<KS>;
-    const size_t smem = Cfg::smem_bytes();
-    static KernelConfig kcfg;
-    const int ctas_per_sm = kcfg.get(kern, smem, Cfg::NT);
-    if (ctas_per_sm < 0) return 1;
-    const size_t gi_bytes = sizeof(float) * (size_t)p.B * p.C * (p.Ho + KS - 1) * (p.Wo + KS - 1);
-    cudaError_t e = cudaMemsetAsync(p.gin, 0, gi_bytes, st);  // the kernel accumulates with red.global
-    if (e != cudaSuccess) {
-        set_error("sepconv_bwd_i_v3: memset: %s", cudaGetErrorString(e));
-        return TAI_ERR_CUDA;
-    }
-    long ctas = (long)p.B * p.nty * p.ntx;
-    const long resident = (long)sm_count() * ctas_per_sm;
-    if (ctas > resident) ctas = resident;
-    double fl, by;
-    gi_work(p, &fl, &by);
-    {
-        TimingScope ts("sepconv_bwd_i", st, fl, by);
-        kern<<<(unsigned)ctas, Cfg::NT, smem, st>>>(maps, p);
-    }
-    note_path("bwd_i:v3");
-    return check_launch("sepconv_bwd_i_v3_kernel");
-}
-
-// Same data movement, cheaper reduction of the warp rows (sepconv_bwd_i_v4.cuh).
+// Persistent TMA-fed scatter kernel for gI (sepconv_bwd_i_v4.cuh); +1 = not TMA-describable, fall back.
 template <int KS, bool FOLD>
 static int launch_gi_v4(const BwdParams &p0, cudaStream_t st)
 {
@@ -577,8 +538,6 @@ static int launch_gi_v4(const BwdParams &p0, cudaStream_t st)
 template <int KS>
 static int launch_gi_tma(const BwdParams &p, cudaStream_t st)
 {
-    static const bool use_v3 = getenv("TAI_GI_V3") != nullptr;  // A/B switch while v4 is being measured
-    if (use_v3) return launch_gi_v3<KS>(p, st);
     return p.C == 1 ? launch_gi_v4<KS, true>(p, st) : launch_gi_v4<KS, false>(p, st);
 }
 
