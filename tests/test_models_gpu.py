@@ -100,6 +100,15 @@ def test_training_environment_step_runs_and_updates(cuda):
     snap = torch.load("/tmp/tai_b200_test/t/model_latest.ckpt", map_location="cpu")
     assert set(snap) == {'updates', 'sum_avg_psnr_err', 'sum_avg_ssim_err', 'generator', 'optimizer_G',
                          'discriminator', 'optimizer_D'}  # environments.py:186-194, 290-297
+    # The reference's train loop hands numpy scalars to save() (train.py:163: np.sum(np.mean(...))) and its published
+    # checkpoints hold them: save() must store plain numbers, load() must accept a checkpoint that holds numpy ones.
+    env.save('model_latest.ckpt', np.int64(7), np.float64(1.5), np.sum(np.mean(np.ones((2, 3)), axis=0)))
+    snap = torch.load("/tmp/tai_b200_test/t/model_latest.ckpt", map_location="cpu")      # weights_only default: loads
+    assert type(snap['updates']) is int and type(snap['sum_avg_psnr_err']) is float and snap['sum_avg_ssim_err'] == 3.0
+    snap['sum_avg_psnr_err'], snap['updates'] = np.float64(2.5), np.int64(9)               # a reference-style checkpoint
+    torch.save(snap, "/tmp/tai_b200_test/t/model_ref_style.ckpt")
+    env.load('model_ref_style.ckpt')
+    assert env.start_update == 9 and env.start_sum_avg_psnr_err == 2.5
 
 
 @pytest.mark.parametrize("key", ["tai", "slomo"])
