@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r02}
-OURS='regex:tai::'
+OURS='regex:sepconv|gates|reppad|bias_act|maxpool|unpool|upsample|l2_gdl|l2_normalize|gather_concat|gray_diff|grad_mix|slomo_|warp_|frames_to_u8'
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_full_line.json 2> gpurun_out/${TAG}_bench_full_line.err; echo "bench rc=$?"
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_reference_arm.err; echo "ref rc=$?"

@@ -46,6 +46,8 @@ def main():
     cases = {
         "kth": (32, 1, 128, 128, 51), "kth1": (1, 1, 128, 128, 51), "kth160": (160, 1, 128, 128, 51), "ucf": (8, 3, 240, 320, 51),
         "small": (16, 1, 128, 128, 13), "mid": (16, 3, 256, 256, 25),
+        # launch shapes of the inference workloads (the kernel network runs once over the T*B middle frames)
+        "ucf24": (24, 3, 240, 320, 51), "kth5": (5, 1, 128, 128, 51),
     }
     g = torch.Generator(device=dev).manual_seed(0)
     U = lambda *s: torch.rand(*s, device=dev, generator=g) * 2 - 1

@@ -504,10 +504,12 @@ maxpool2x2_bwd_kernel(const float *__restrict__ gout, const unsigned char *__res
     }
 }
 
-static int resample_args_ok(const char *who, const void *a, const void *b, long long N, int H, int W)
+// `scale`: elements of the LARGEST tensor of the call per H x W plane element (4 where H x W is the low-resolution
+// side of an up / down-sampling pair, 1 where it is the high-resolution side)
+static int resample_args_ok(const char *who, const void *a, const void *b, long long N, int H, int W, int scale = 4)
 {
     TAI_REQUIRE(a && b && N > 0 && H > 0 && W > 0, TAI_ERR_INVALID_ARGUMENT, "%s: bad arguments N=%lld H=%d W=%d", who, N, H, W);
-    TAI_REQUIRE(fits_int31(N * 4LL * H * W), TAI_ERR_TOO_LARGE, "%s: tensor has >= 2^31 elements", who);
+    TAI_REQUIRE(fits_int31(N * (long long)scale * H * W), TAI_ERR_TOO_LARGE, "%s: tensor has >= 2^31 elements", who);
     return TAI_OK;
 }
 
@@ -607,7 +609,7 @@ extern "C" int unpool_backward_b200(const float *grad_out, float *grad_x, long l
 
 extern "C" int maxpool2x2_forward_b200(const float *in, float *out, unsigned char *code, long long N, int H, int W, void *stream)
 {
-    int rc = resample_args_ok("maxpool2x2_forward_b200", in, out, N, H, W);
+    int rc = resample_args_ok("maxpool2x2_forward_b200", in, out, N, H, W, 1);
     if (rc != TAI_OK) return rc;
     TAI_REQUIRE(code != nullptr && H >= 2 && W >= 2, TAI_ERR_INVALID_ARGUMENT, "maxpool2x2_forward_b200: needs H, W >= 2 and a code buffer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -623,7 +625,7 @@ extern "C" int maxpool2x2_forward_b200(const float *in, float *out, unsigned cha
 extern "C" int maxpool2x2_backward_b200(const float *grad_out, const unsigned char *code, float *grad_in, long long N, int H, int W,
                                         void *stream)
 {
-    int rc = resample_args_ok("maxpool2x2_backward_b200", grad_out, grad_in, N, H, W);
+    int rc = resample_args_ok("maxpool2x2_backward_b200", grad_out, grad_in, N, H, W, 1);
     if (rc != TAI_OK) return rc;
     TAI_REQUIRE(code != nullptr && H >= 2 && W >= 2, TAI_ERR_INVALID_ARGUMENT, "maxpool2x2_backward_b200: needs H, W >= 2 and a code buffer");
     cudaStream_t st = (cudaStream_t)stream;
