@@ -147,7 +147,7 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
         // ---- halo of all CG (== C) channels ----
         {
             constexpr int NK = (PITCH + 31) / 32;
-            constexpr int RB = 4;
+            constexpr int RB = (ROWS + Cfg::NT / 32 - 1) / (Cfg::NT / 32);  // all rows of a warp in one batch: one memory round trip
             int coff[NK];
             bool cok[NK];
 #pragma unroll

@@ -28,6 +28,10 @@
 #include "sepconv_common.cuh"
 #include "tma.cuh"
 
+#ifndef TAI_HALO_RB
+#define TAI_HALO_RB ((Cfg::ROWS + Cfg::NT / 32 - 1) / (Cfg::NT / 32))
+#endif
+
 namespace tai {
 
 #ifdef TAI_LAB_TIMING
@@ -166,7 +170,11 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                     }
                     // LDG -> STS in register batches (an LDGSTS costs ~8 LSU cycles, LDG + STS ~3)
                     constexpr int NK = (PITCH + 31) / 32;
-                    constexpr int RB = 4;  // rows per batch and warp
+                    // rows per batch and warp.  Single stream: ALL of a warp's rows in one batch (the H registers are not
+                    // live yet, so 45 staging registers are free): one memory round trip per tile instead of four
+                    // (0.406 -> 0.393 ms at B = 160).  The dual-stream kernel keeps 4-row batches: with the first
+                    // stream's results live the large batch costs more than it hides (0.790 -> 0.867 ms, measured).
+                    constexpr int RB = DUAL ? 4 : TAI_HALO_RB;
                     for (int c = 0; c < CG; ++c) {
                         const float *src = PAD ? in + ((long)(b * p.C + c0 + c)) * plane
                                                : in + ((long)(b * p.C + c0 + c)) * Hi * Wi;
