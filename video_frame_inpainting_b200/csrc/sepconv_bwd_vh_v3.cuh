@@ -11,9 +11,13 @@
 //     a_r[j] += (V_i * gO_c) * I[yy][x+j]               -> gH_j, complete inside the lane
 // The same shared-memory word of I feeds both FMAs.  The four partial s_r are combined by a 3-shuffle
 // reduce-scatter after which lane group ch holds the total of output row r = ch and stores it.
-// Data movement is that of sepconv_fwd_v3.cuh: H box -> slab (TMA) -> registers, slab refilled with the
-// V box in three tap chunks, next tile's boxes prefetched into L2, halo staged by LDG/STS with the
-// replication pad optionally folded in.
+// Data movement: as in sepconv_fwd_v3.cuh the H box arrives by TMA and is copied to registers, the V box
+// streams in as three tap chunks, the halo is staged by LDG/STS with the replication pad optionally folded in.
+// The 4-row boxes are half the size of the forward kernel's, so H and V get a slab EACH (2 x 26 KB + 18 KB of
+// halo still fit three CTAs per SM): the V chunks of a tile are requested at its very start (their slab was
+// released by the barrier that ended the previous tile) and the H box of the NEXT tile is requested as soon as
+// this tile's taps are in registers -- it has the whole sweep to arrive.  Neither TMA latency is on the
+// critical path any more (round 1 time-shared one slab: H wait + V wait were serial phases of every tile).
 #pragma once
 
 #include "common.cuh"
@@ -49,7 +53,8 @@ struct VhV3Cfg {
     static constexpr int VROW = TILE_H * TILE_W;
     static constexpr int SLAB_FLOATS = NCHUNK * CH_TAPS * VROW;
     static constexpr int NBAR = 1 + NCHUNK;
-    static constexpr size_t smem_bytes(int cg) { return (size_t)(SLAB_FLOATS + cg * ROWS * PITCH) * 4 + 8 * NBAR; }
+    static constexpr int HSLAB_FLOATS = KS * VROW;                 // the H box has a slab of its own (see the kernel)
+    static constexpr size_t smem_bytes(int cg) { return (size_t)(SLAB_FLOATS + HSLAB_FLOATS + cg * ROWS * PITCH) * 4 + 8 * NBAR; }
 };
 
 struct VhV3Maps {
@@ -107,8 +112,9 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
     constexpr int J = Cfg::J, PITCH = Cfg::PITCH, ROWS = Cfg::ROWS, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
     constexpr int CSTRIDE = ROWS * PITCH;
     extern __shared__ __align__(128) float smem[];
-    float *slab = smem;
-    float *is = smem + Cfg::SLAB_FLOATS;
+    float *slab = smem;                                  // V chunks of the current tile
+    float *hslab = smem + Cfg::SLAB_FLOATS;              // H box of the current tile, then of the next one
+    float *is = hslab + Cfg::HSLAB_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(is + CG * CSTRIDE);
 
     const int Ho = p.Ho, Wo = p.Wo;
@@ -119,30 +125,43 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
     const long plane = (long)Ho * Wo;
     const int ntiles = p.B * p.nty * p.ntx;
 
+    // tile index -> (x0, y0, b); tiles that would stick out are shifted back inside
+    auto tile_origin = [&](int tile, int &x0, int &y0, int &b) {
+        const int tx = tile % p.ntx;
+        tile /= p.ntx;
+        x0 = max(0, min(tx * TILE_W, Wo - TILE_W));
+        y0 = min((tile % p.nty) * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
+        b = tile / p.nty;
+    };
+
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
+        if ((int)blockIdx.x < ntiles) {   // H box of this CTA's first tile
+            int fx, fy, fb;
+            tile_origin(blockIdx.x, fx, fy, fb);
+            mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
+            tma_load_4d(hslab, &maps.h, &bars[0], fx, fy, 0, fb);
+        }
     }
     __syncthreads();
     uint32_t parity = 0;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int t = tile;
-        const int tx = t % p.ntx;
-        t /= p.ntx;
-        const int ty = t % p.nty;
-        const int b = t / p.nty;
-        const int x0 = max(0, min(tx * TILE_W, Wo - TILE_W));
-        const int y0 = min(ty * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
+        int x0, y0, b;
+        tile_origin(tile, x0, y0, b);
         const int px_raw = x0 + warp * FNX + cx;
         const bool px_ok = px_raw < Wo;
         const int px = px_ok ? px_raw : Wo - 1;
 
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) {   // V chunks of this tile: their slab was released by the barrier that ended the last tile
             fence_proxy_async();
-            mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
-            tma_load_4d(slab, &maps.h, &bars[0], x0, y0, 0, b);
+#pragma unroll
+            for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                mbar_expect_tx(&bars[1 + q], Cfg::CH_TAPS * Cfg::VROW * 4);
+                tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v, &bars[1 + q], x0, y0, q * Cfg::CH_TAPS, b);
+            }
         }
         // ---- halo of all CG (== C) channels ----
         {
@@ -190,11 +209,11 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
 #pragma unroll
             for (int r = 0; r < BP; ++r) go[c][r] = __ldg(p.gout + ((long)(b * CG + c) * Ho + y0 + r) * Wo + px);
 
-        // ---- H taps: slab -> registers ----
+        // ---- H taps: slab -> registers (the box was requested during the previous tile) ----
         mbar_wait(&bars[0], parity);
         float h[BP][J], a[BP][J];
         {
-            const float *hs = slab + ch * Cfg::VROW + warp * FNX + cx;
+            const float *hs = hslab + ch * Cfg::VROW + warp * FNX + cx;
 #pragma unroll
             for (int jj = 0; jj < J; ++jj)
 #pragma unroll
@@ -203,25 +222,16 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
                     a[r][jj] = 0.f;
                 }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        __syncthreads();  // H is in registers everywhere; the halo is complete
+        if (threadIdx.x == 0 && tile + (int)gridDim.x < ntiles) {
+            // the H box of the next tile into the slab that has just been read out, its V chunks into L2
+            int nx0, ny0, nb;
+            tile_origin(tile + gridDim.x, nx0, ny0, nb);
             fence_proxy_async();
+            mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
+            tma_load_4d(hslab, &maps.h, &bars[0], nx0, ny0, 0, nb);
 #pragma unroll
-            for (int q = 0; q < Cfg::NCHUNK; ++q) {
-                mbar_expect_tx(&bars[1 + q], Cfg::CH_TAPS * Cfg::VROW * 4);
-                tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v, &bars[1 + q], x0, y0, q * Cfg::CH_TAPS, b);
-            }
-            if (tile + (int)gridDim.x < ntiles) {
-                int n = tile + gridDim.x;
-                const int ntx_ = n % p.ntx;
-                n /= p.ntx;
-                const int nty_ = n % p.nty;
-                const int nb = n / p.nty;
-                const int nx0 = max(0, min(ntx_ * TILE_W, Wo - TILE_W)), ny0 = min(nty_ * TILE_H, Ho - TILE_H);
-                tma_prefetch_l2_4d(&maps.h, nx0, ny0, 0, nb);
-#pragma unroll
-                for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
-            }
+            for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
         }
 
         const float *srow = is + warp * FNX + cx + ch;
