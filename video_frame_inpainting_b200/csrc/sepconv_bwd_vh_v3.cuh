@@ -125,32 +125,41 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
     const long plane = (long)Ho * Wo;
     const int ntiles = p.B * p.nty * p.ntx;
 
+    // Tiles are numbered with the ROW index fastest and every CTA walks a contiguous range, so the next tile is
+    // usually the one directly below: it shares ks-1 of its ks+3 halo rows with the current one, and only the 4
+    // new rows are staged (cp.async) into the ring slots the sweep no longer needs -- the halo staging of 54 rows
+    // per 4 output rows was the longest phase between two sweeps.
     // tile index -> (x0, y0, b); tiles that would stick out are shifted back inside
     auto tile_origin = [&](int tile, int &x0, int &y0, int &b) {
-        const int tx = tile % p.ntx;
-        tile /= p.ntx;
-        x0 = max(0, min(tx * TILE_W, Wo - TILE_W));
-        y0 = min((tile % p.nty) * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
-        b = tile / p.nty;
+        const int ty = tile % p.nty;
+        tile /= p.nty;
+        x0 = max(0, min((tile % p.ntx) * TILE_W, Wo - TILE_W));
+        y0 = min(ty * TILE_H, Ho - TILE_H);  // host guarantees Ho >= TILE_H
+        b = tile / p.ntx;
     };
+    const int t_lo = (int)((long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long)ntiles * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
-        if ((int)blockIdx.x < ntiles) {   // H box of this CTA's first tile
+        if (t_lo < t_hi) {   // H box of this CTA's first tile
             int fx, fy, fb;
-            tile_origin(blockIdx.x, fx, fy, fb);
+            tile_origin(t_lo, fx, fy, fb);
             mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
             tma_load_4d(hslab, &maps.h, &bars[0], fx, fy, 0, fb);
         }
     }
     __syncthreads();
     uint32_t parity = 0;
+    int rbase = 0;                          // ring row that holds halo row 0 of the current tile
+    int px0 = -1, py0 = -1, pb = -1;        // origin of the previous tile
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = t_lo; tile < t_hi; ++tile) {
         int x0, y0, b;
         tile_origin(tile, x0, y0, b);
+        const bool walk = (b == pb && x0 == px0 && y0 == py0 + TILE_H);
+        px0 = x0; py0 = y0; pb = b;
         const int px_raw = x0 + warp * FNX + cx;
         const bool px_ok = px_raw < Wo;
         const int px = px_ok ? px_raw : Wo - 1;
@@ -163,10 +172,9 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
                 tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v, &bars[1 + q], x0, y0, q * Cfg::CH_TAPS, b);
             }
         }
-        // ---- halo of all CG (== C) channels ----
+        // ---- halo of all CG (== C) channels: everything for a new column, the 4 new rows when walking down ----
         {
             constexpr int NK = (PITCH + 31) / 32;
-            constexpr int RB = (ROWS + Cfg::NT / 32 - 1) / (Cfg::NT / 32);  // all rows of a warp in one batch: one memory round trip
             int coff[NK];
             bool cok[NK];
 #pragma unroll
@@ -180,24 +188,47 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
                     coff[k] = cok[k] ? gx : 0;
                 }
             }
-            for (int c = 0; c < CG; ++c) {
-                const float *src = PAD ? p.in + ((long)(b * CG + c)) * plane : p.in + ((long)(b * CG + c)) * Hi * Wi;
-                for (int ry0 = warp * RB; ry0 < ROWS; ry0 += (Cfg::NT / 32) * RB) {
-                    float tmp[RB][NK];
-#pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        const int gy = y0 + min(ry0 + q, ROWS - 1);
+            if (walk) {
+                rbase += TILE_H;
+                if (rbase >= ROWS) rbase -= ROWS;
+                // halo rows ROWS-4..ROWS-1 of this tile -> the ring slots of the previous tile's rows 0..3 (asynchronous:
+                // they are first read at sweep row ROWS-4; waited for at the start of the last V chunk)
+                for (int c = 0; c < CG; ++c) {
+                    const float *src = PAD ? p.in + ((long)(b * CG + c)) * plane : p.in + ((long)(b * CG + c)) * Hi * Wi;
+                    for (int ry = ROWS - TILE_H + warp; ry < ROWS; ry += Cfg::NT / 32) {
+                        const int gy = y0 + ry;
                         const float *grow = PAD ? src + (long)clampi(gy - KS / 2, 0, Ho - 1) * Wo : src + (long)gy * Wi;
+                        int rr = rbase + ry;
+                        if (rr >= ROWS) rr -= ROWS;
+                        float *drow = is + c * CSTRIDE + rr * PITCH + lane;
 #pragma unroll
-                        for (int k = 0; k < NK; ++k) tmp[q][k] = cok[k] ? __ldg(grow + coff[k]) : 0.f;
+                        for (int k = 0; k < NK; ++k)
+                            if (lane + 32 * k < PITCH) cp_async_f32(drow + 32 * k, grow + coff[k], cok[k]);
                     }
+                }
+                cp_async_commit();
+            } else {
+                rbase = 0;
+                constexpr int RB = (ROWS + Cfg::NT / 32 - 1) / (Cfg::NT / 32);  // all rows of a warp in one batch: one memory round trip
+                for (int c = 0; c < CG; ++c) {
+                    const float *src = PAD ? p.in + ((long)(b * CG + c)) * plane : p.in + ((long)(b * CG + c)) * Hi * Wi;
+                    for (int ry0 = warp * RB; ry0 < ROWS; ry0 += (Cfg::NT / 32) * RB) {
+                        float tmp[RB][NK];
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        if (ry0 + q < ROWS) {
-                            float *drow = is + c * CSTRIDE + (ry0 + q) * PITCH + lane;
+                        for (int q = 0; q < RB; ++q) {
+                            const int gy = y0 + min(ry0 + q, ROWS - 1);
+                            const float *grow = PAD ? src + (long)clampi(gy - KS / 2, 0, Ho - 1) * Wo : src + (long)gy * Wi;
 #pragma unroll
-                            for (int k = 0; k < NK; ++k)
-                                if (lane + 32 * k < PITCH) drow[32 * k] = tmp[q][k];
+                            for (int k = 0; k < NK; ++k) tmp[q][k] = cok[k] ? __ldg(grow + coff[k]) : 0.f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) {
+                            if (ry0 + q < ROWS) {
+                                float *drow = is + c * CSTRIDE + (ry0 + q) * PITCH + lane;
+#pragma unroll
+                                for (int k = 0; k < NK; ++k)
+                                    if (lane + 32 * k < PITCH) drow[32 * k] = tmp[q][k];
+                            }
                         }
                     }
                 }
@@ -223,10 +254,10 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
                 }
         }
         __syncthreads();  // H is in registers everywhere; the halo is complete
-        if (threadIdx.x == 0 && tile + (int)gridDim.x < ntiles) {
+        if (threadIdx.x == 0 && tile + 1 < t_hi) {
             // the H box of the next tile into the slab that has just been read out, its V chunks into L2
             int nx0, ny0, nb;
-            tile_origin(tile + gridDim.x, nx0, ny0, nb);
+            tile_origin(tile + 1, nx0, ny0, nb);
             fence_proxy_async();
             mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
             tma_load_4d(hslab, &maps.h, &bars[0], nx0, ny0, 0, nb);
@@ -234,9 +265,14 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
         }
 
-        const float *srow = is + warp * FNX + cx + ch;
+        const float *sbase = is + warp * FNX + cx + ch;
         const float *vrow = slab + warp * FNX + cx;
         float *gv = p.gver ? p.gver + ((long)b * KS * Ho + y0 + ch) * Wo + px : nullptr;  // + tap * plane
+        auto ring_row = [&](int yy) {   // halo row yy of this tile inside the ring
+            int rr = rbase + yy;
+            if (rr >= ROWS) rr -= ROWS;
+            return sbase + rr * PITCH;
+        };
 
         // After one input row: combine the four tap groups and store gV[tap yy-ch][row ch].
         auto finish_row = [&](int yy, float (&tsum)[BP]) {
@@ -257,7 +293,7 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
         static_for<0, BP - 1>([&](auto YY) {
             constexpr int yy = decltype(YY)::value;
             float tsum[BP];
-            vh_row_v3<KS, CG, 0, yy + 1>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+            vh_row_v3<KS, CG, 0, yy + 1>(ring_row(yy), vrow + yy * Cfg::VROW, h, a, go, tsum);
             finish_row(yy, tsum);
         });
 #pragma unroll
@@ -265,17 +301,25 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             const int lo = max(BP - 1, q * Cfg::CH_TAPS);
             const int hi = (q == Cfg::NCHUNK - 1) ? KS : min(KS, (q + 1) * Cfg::CH_TAPS);
             if (q >= PRO_CHUNKS) mbar_wait(&bars[1 + q], parity);
+            if (q == Cfg::NCHUNK - 1 && walk) {   // the 4 new halo rows are first read at row ROWS-4 >= lo
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            const float *srow = ring_row(lo);
+            const float *wrap = sbase + ROWS * PITCH;
 #pragma unroll 1
             for (int yy = lo; yy < hi; ++yy) {
                 float tsum[BP];
-                vh_row_v3<KS, CG, 0, BP>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+                vh_row_v3<KS, CG, 0, BP>(srow, vrow + yy * Cfg::VROW, h, a, go, tsum);
                 finish_row(yy, tsum);
+                srow += PITCH;
+                if (srow >= wrap) srow -= ROWS * PITCH;
             }
         }
         static_for<0, BP - 1>([&](auto E) {
             constexpr int yy = KS + decltype(E)::value;
             float tsum[BP];
-            vh_row_v3<KS, CG, decltype(E)::value + 1, BP>(srow + yy * PITCH, vrow + yy * Cfg::VROW, h, a, go, tsum);
+            vh_row_v3<KS, CG, decltype(E)::value + 1, BP>(ring_row(yy), vrow + yy * Cfg::VROW, h, a, go, tsum);
             finish_row(yy, tsum);
         });
         parity ^= 1;
