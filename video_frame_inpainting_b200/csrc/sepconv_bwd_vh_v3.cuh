@@ -274,17 +274,22 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             return sbase + rr * PITCH;
         };
 
-        // After one input row: combine the four tap groups and store gV[tap yy-ch][row ch].
-        auto finish_row = [&](int yy, float (&tsum)[BP]) {
+        const bool gv_ok = gv != nullptr && px_ok;
+        // After one input row: combine the four tap groups (lane group ch ends up with the total of output row ch) ...
+        auto reduce_rows = [&](float (&tsum)[BP]) {
             const float keep0 = hi16 ? tsum[2] : tsum[0];
             const float keep1 = hi16 ? tsum[3] : tsum[1];
             const float send0 = hi16 ? tsum[0] : tsum[2];
             const float send1 = hi16 ? tsum[1] : tsum[3];
             const float u0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 16);
             const float u1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
-            const float tot = (hi8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, hi8 ? u0 : u1, 8);
+            return (hi8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, hi8 ? u0 : u1, 8);
+        };
+        // ... and store gV[tap yy-ch][row ch] (prologue / epilogue rows: the tap may fall outside [0, ks))
+        auto finish_row = [&](int yy, float (&tsum)[BP]) {
+            const float tot = reduce_rows(tsum);
             const int i = yy - ch;
-            if (gv && px_ok && i >= 0 && i < KS) gv[(long)i * plane] = tot;
+            if (gv_ok && i >= 0 && i < KS) gv[(long)i * plane] = tot;
         };
 
         constexpr int PRO_CHUNKS = (BP - 2) / Cfg::CH_TAPS + 1;  // chunks touched by the prologue rows
@@ -307,11 +312,17 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             }
             const float *srow = ring_row(lo);
             const float *wrap = sbase + ROWS * PITCH;
+            // steady rows: every lane's tap yy - ch is inside [0, ks), the store pointer just walks one tap plane per row
+            float *gvp = gv_ok ? gv + (long)(lo - ch) * plane : nullptr;
 #pragma unroll 1
             for (int yy = lo; yy < hi; ++yy) {
                 float tsum[BP];
                 vh_row_v3<KS, CG, 0, BP>(srow, vrow + yy * Cfg::VROW, h, a, go, tsum);
-                finish_row(yy, tsum);
+                const float tot = reduce_rows(tsum);
+                if (gv_ok) {
+                    *gvp = tot;
+                    gvp += plane;
+                }
                 srow += PITCH;
                 if (srow >= wrap) srow -= ROWS * PITCH;
             }
