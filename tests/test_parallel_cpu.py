@@ -95,3 +95,39 @@ def test_single_process_reducer_is_a_noop():
     red.finish()
     assert torch.allclose(net.weight.grad, torch.full((2, 4), 3.0))
     assert net.weight.grad.data_ptr() >= red.flat.data_ptr()
+
+
+def test_buckets_are_reduced_in_index_order_whatever_the_hook_order(monkeypatch):
+    """Every rank must issue the same sequence of collectives even when its gradient hooks complete in another order
+    (a graph that differs between ranks, unused parameters): bucket i is launched only after buckets 0..i-1."""
+    import video_frame_inpainting_b200.parallel as par
+    net = torch.nn.Sequential(*[torch.nn.Linear(8, 8) for _ in range(4)])
+    red = FlatGradAllReducer(net, n_buckets=4)
+    assert len(red.buckets) >= 3
+    launched = []
+
+    class _Done(object):
+        def wait(self):
+            pass
+
+    def fake_all_reduce(t, op=None, async_op=False):
+        launched.append((t.data_ptr() - red.flat.data_ptr()) // 4)
+        return _Done()
+    monkeypatch.setattr(par.dist, "all_reduce", fake_all_reduce)
+    monkeypatch.setattr(par.dist, "get_world_size", lambda: 2)
+    monkeypatch.setattr(FlatGradAllReducer, "active", property(lambda self: True))
+    starts = [lo for lo, _ in red._slices]
+    # hooks arrive bucket-reversed: nothing may be launched until bucket 0 is complete, then all of them in index order
+    red.arm()
+    for bucket in reversed(red.buckets):
+        for p in bucket:
+            red._hook(p)
+    assert launched == starts
+    # a bucket whose hooks never fire (unused parameters) is flushed by finish(), still in index order
+    launched.clear()
+    red.arm()
+    for p in red.buckets[1]:
+        red._hook(p)
+    assert launched == []
+    red.finish()
+    assert launched == starts
