@@ -132,7 +132,9 @@ def test_slomo_fused_stages(cuda, B, C, H, W, T):
         assert_close(out, ref, tol=2e-3, what="refine+blend")
 
 
-@pytest.mark.parametrize("B,C,H,W,T", [(1, 3, 32, 64, 3), (2, 1, 16, 24, 5), (2, 2, 12, 20, 1)])
+@pytest.mark.parametrize("B,C,H,W,T", [(1, 3, 32, 64, 3), (2, 1, 16, 24, 5), (2, 2, 12, 20, 1),
+                                       (2, 3, 20, 40, 2),     # four-pixel kernels: ragged tiles in x and in y
+                                       (1, 3, 10, 18, 2)])    # W % 4 != 0: per-pixel kernels
 def test_slomo_time_batched_stages_forward_and_backward(cuda, B, C, H, W, T):
     """slomo.py:307-340 as two launches over all T middle frames (slomo_interp_input_*, slomo_refine_blend_batched_*):
     values against the float64 oracle, BIT-EXACT against the per-t kernels (same arithmetic, other launch shape),

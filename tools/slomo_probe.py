@@ -22,7 +22,7 @@ flush = torch.empty(64 * 1024 * 1024, device=dev)
 times = {}
 for it in range(4):
     flush.zero_()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     ev[0].record()
     X, c0, c1 = ops.SlomoInterpInputFunction.apply(i0, i1, f01, f10, T)
     ev[1].record()
@@ -31,12 +31,12 @@ for it in range(4):
     gp = torch.ones_like(pred)
     gx = torch.ones_like(X)
     flush.zero_()
-    ev[2].record()
+    ev[4].record()
     grads = torch.autograd.grad([pred, X], [d0, d1, v0, f01, f10], [gp, gx])
-    ev[3].record()
+    ev[5].record()
     torch.cuda.synchronize()
     if it:
         times.setdefault("interp_input_us", []).append(ev[0].elapsed_time(ev[1]) * 1e3)
         times.setdefault("refine_blend_us", []).append(ev[1].elapsed_time(ev[2]) * 1e3)
-        times.setdefault("both_backward_us", []).append(ev[2].elapsed_time(ev[3]) * 1e3)
+        times.setdefault("both_backward_us", []).append(ev[4].elapsed_time(ev[5]) * 1e3)
 print(json.dumps({k: min(v) for k, v in times.items()}))

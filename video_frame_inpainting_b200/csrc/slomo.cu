@@ -363,154 +363,251 @@ slomo_refine_blend_t_bwd_kernel(const float *__restrict__ i0, const float *__res
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same two kernels with the frames staged in shared memory.  The refined flows are clamped to [-1, 1] pixel
-// (slomo.py:320-321), and ix = (x + u) (W-1)/W, so the four taps of pixel (x, y) lie in columns x-2..x+1 and rows
-// y-2..y+1 whatever the inputs: a CTA that owns a 32 x 8 pixel tile needs a 35 x 11 patch of I0 and of I1 per channel.
-// The patch is loaded ONCE per tile (coalesced, zero-filled outside the image: the sampler's zero padding) and serves
-// all T time steps; what is left per step are the nine streamed operands.  This removes the second, dependent memory
-// round trip of the gather formulation (streamed flows -> 24 gather addresses), which is what held it at 46 % of the
-// HBM peak (`long_scoreboard` 5.3 per issue).  Integer logic unchanged: floor() and the tap weights come from the
-// same FP32 coordinate chain; only the address of a tap is formed relative to the patch.
-constexpr int kSbTW = 32, kSbTH = 8, kSbHaloLo = 2, kSbPW = kSbTW + 3, kSbPH = kSbTH + 3, kSbPitch = 36;
+// The same two kernels for W % 4 == 0 and C in {1, 3}: FOUR adjacent pixels per thread and the frames staged in
+// shared memory.  The per-pixel kernels above are issue-bound, not latency-bound (ncu: 25 M warp instructions for
+// 2 M pixel-steps = 400 per pixel-step, issue slots 57 % busy, DRAM 25 %): 64-bit address arithmetic for nine
+// streamed loads, 24 predicated gathers and three stores per pixel-step outweighs the ~120 FP instructions of
+// the coordinate chains and the blend.  With four pixels per thread the streamed operands move as 128-bit
+// accesses (a quarter of the address arithmetic).  The refined flows are clamped to [-1, 1] pixel (slomo.py:
+// 320-321) and ix = (x + u)(W-1)/W, so the four taps of pixel (x, y) lie in columns x-2..x+1 and rows y-2..y+1
+// whatever the inputs: a CTA that owns a 32 x 16 pixel tile stages a 35 x 19 patch of I0 and of I1 per channel
+// ONCE (zero-filled outside the image: the sampler's zero padding, so taps need no validity predicates) and
+// uses it for all T steps.  Warp = 4 rows x 8 threads; patch pitch 37 makes the bank of a tap 4 tx + 5 r + const:
+// conflict-free when the lanes' displacements agree.  floor() and the tap weights come from the same FP32
+// coordinate chain as everywhere else; only the address of a tap is formed relative to the patch.
+constexpr int kQW = 32, kQH = 16, kQLo = 2, kQPW = kQW + 3, kQPH = kQH + 3, kQPitch = 37, kQThreads = 128;
 
 template <int CT>
 __device__ __forceinline__ void refine_stage_patch(float *patch, const float *__restrict__ i0, const float *__restrict__ i1,
                                                    int b, int tx0, int ty0, int H, int W)
 {
+    // Same thread -> (row, quad) mapping as the compute phase: a 128-bit load per (plane, row, quad) for the 32
+    // interior columns, the quads at the tile's edges add the two left and the one right halo columns.  Loads go
+    // to clamped (always valid) addresses and are zeroed by selects: no divergent branches around them.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tx = lane & 7, r = lane >> 3;
     const int hw = H * W;
-    constexpr int PLANE = kSbPH * kSbPitch;
-    for (int e = threadIdx.x; e < 2 * CT * PLANE; e += 256) {
-        const int plane = e / PLANE, r = e - plane * PLANE;
-        const int ry = r / kSbPitch, rx = r - ry * kSbPitch;
-        const int gy = ty0 - kSbHaloLo + ry, gx = tx0 - kSbHaloLo + rx;
-        const int img = plane / CT, ch = plane - img * CT;
-        float v = 0.f;
-        if (rx < kSbPW && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
-            v = __ldg((img ? i1 : i0) + ((long)b * CT + ch) * hw + (long)gy * W + gx);
-        patch[e] = v;
+    const int x = tx0 + 4 * tx;
+    const bool okx = x < W;                                   // W % 4 == 0
+    const bool left = tx == 0 && tx0 > 0, right = tx == 7 && tx0 + kQW < W;
+    const float *b0 = i0 + (long)b * CT * hw, *b1 = i1 + (long)b * CT * hw;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ry = pass * 16 + 4 * warp + r;
+        if (ry < kQPH) {                                      // second pass: patch rows 16..18 only
+            const int gy = ty0 - kQLo + ry;
+            const bool ok = (unsigned)gy < (unsigned)H && okx;
+            const int off = min(max(gy, 0), H - 1) * W + (okx ? x : 0);
+            float4 v[2 * CT];
+            float2 vl[2 * CT];
+            float vr[2 * CT];
+#pragma unroll
+            for (int plane = 0; plane < 2 * CT; ++plane) {
+                const float *src = (plane >= CT ? b1 + (plane - CT) * hw : b0 + plane * hw) + off;
+                v[plane] = __ldg(reinterpret_cast<const float4 *>(src));
+                vl[plane] = make_float2(0.f, 0.f);
+                vr[plane] = 0.f;
+                if (left) vl[plane] = __ldg(reinterpret_cast<const float2 *>(src - 2));
+                if (right) vr[plane] = __ldg(src + 4);
+            }
+            float *dst = patch + ry * kQPitch + kQLo + 4 * tx;
+#pragma unroll
+            for (int plane = 0; plane < 2 * CT; ++plane) {
+                float *d = dst + plane * (kQPH * kQPitch);
+                d[0] = ok ? v[plane].x : 0.f; d[1] = ok ? v[plane].y : 0.f;
+                d[2] = ok ? v[plane].z : 0.f; d[3] = ok ? v[plane].w : 0.f;
+                if (tx == 0) { d[-2] = ok ? vl[plane].x : 0.f; d[-1] = ok ? vl[plane].y : 0.f; }
+                if (tx == 7) d[4] = ok ? vr[plane] : 0.f;
+            }
+        }
     }
+}
+
+struct RefineIn4 {
+    float4 d0u, d0v, d1u, d1v, f0u, f0v, f1u, f1v, vis;
+};
+
+__device__ __forceinline__ RefineIn4 refine_load4(const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                                                  const float *__restrict__ d0, const float *__restrict__ d1,
+                                                  const float *__restrict__ v0, int t, int b, int pix, int B, int T, int hw)
+{
+    const long nb = (long)t * B + b;
+    const long du = nb * 2 * hw + pix, fu = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;  // collectors: reversed time
+    auto L = [](const float *p) { return ld_stream4(reinterpret_cast<const float4 *>(p)); };
+    RefineIn4 r;
+    r.d0u = L(d0 + du); r.d0v = L(d0 + du + hw);
+    r.d1u = L(d1 + du); r.d1v = L(d1 + du + hw);
+    r.f0u = L(ft0c + fu); r.f0v = L(ft0c + fu + hw);
+    r.f1u = L(ft1c + fu); r.f1v = L(ft1c + fu + hw);
+    r.vis = L(v0 + nb * hw + pix);
+    return r;
+}
+
+__device__ __forceinline__ float comp(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+__device__ __forceinline__ void set_comp(float4 &v, int j, float a)
+{
+    if (j == 0) v.x = a; else if (j == 1) v.y = a; else if (j == 2) v.z = a; else v.w = a;
 }
 
 // offset of the north-west tap inside a patch plane (the clamp only guards the address against inputs that cannot
 // occur: |flow| <= 1 keeps every tap inside the patch)
 __device__ __forceinline__ int patch_offset(const WarpCoord &c, int tx0, int ty0)
 {
-    const int lx = min(max(c.x0 - (tx0 - kSbHaloLo), 0), kSbPW - 2), ly = min(max(c.y0 - (ty0 - kSbHaloLo), 0), kSbPH - 2);
-    return ly * kSbPitch + lx;
+    const int lx = min(max(c.x0 - (tx0 - kQLo), 0), kQPW - 2), ly = min(max(c.y0 - (ty0 - kQLo), 0), kQPH - 2);
+    return ly * kQPitch + lx;
+}
+
+struct QuadGeom {
+    int tx0, ty0, b, x, y, pix;
+    bool active;
+};
+
+__device__ __forceinline__ QuadGeom quad_geom(int tiles_x, int tiles_y, int H, int W)
+{
+    QuadGeom q;
+    int tile = blockIdx.x;
+    q.tx0 = (tile % tiles_x) * kQW;
+    tile /= tiles_x;
+    q.ty0 = (tile % tiles_y) * kQH;
+    q.b = tile / tiles_y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    q.x = q.tx0 + 4 * (lane & 7);
+    q.y = q.ty0 + 4 * warp + (lane >> 3);
+    q.active = q.x < W && q.y < H;      // W % 4 == 0: a quad is inside or outside as a whole
+    q.pix = q.active ? q.y * W + q.x : 0;
+    return q;
 }
 
 template <int CT>
-__global__ void __launch_bounds__(256)
-slomo_refine_blend_tiled_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
-                                const float *__restrict__ ft0c, const float *__restrict__ ft1c,
-                                const float *__restrict__ d0, const float *__restrict__ d1, const float *__restrict__ v0,
-                                const SlomoTimes tm, float *__restrict__ pred, int B, int tiles_x, int tiles_y, const WarpGeom g)
+__global__ void __launch_bounds__(kQThreads, 4)
+slomo_refine_blend_quad_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                               const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                               const float *__restrict__ d0, const float *__restrict__ d1, const float *__restrict__ v0,
+                               const SlomoTimes tm, float *__restrict__ pred, int B, int tiles_x, int tiles_y, const WarpGeom g)
 {
-    __shared__ float patch[2 * CT * kSbPH * kSbPitch];
-    constexpr int PLANE = kSbPH * kSbPitch;
+    __shared__ float patch[2 * CT * kQPH * kQPitch];
+    constexpr int PLANE = kQPH * kQPitch;
     const int H = g.H, W = g.W, T = tm.T;
     const int hw = H * W;
-    int tile = blockIdx.x;
-    const int tx0 = (tile % tiles_x) * kSbTW;
-    tile /= tiles_x;
-    const int ty0 = (tile % tiles_y) * kSbTH, b = tile / tiles_y;
-    const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
-    const bool active = x < W && y < H;
-    const int pix = active ? y * W + x : 0;
-    RefineIn cur = refine_load(ft0c, ft1c, d0, d1, v0, 0, b, pix, B, T, hw);   // in flight while the patch is staged
-    refine_stage_patch<CT>(patch, i0, i1, b, tx0, ty0, H, W);
+    const QuadGeom q = quad_geom(tiles_x, tiles_y, H, W);
+    RefineIn4 ra = refine_load4(ft0c, ft1c, d0, d1, v0, 0, q.b, q.pix, B, T, hw);   // in flight while the patch is staged
+    refine_stage_patch<CT>(patch, i0, i1, q.b, q.tx0, q.ty0, H, W);
     __syncthreads();
-    if (!active) return;
-    for (int t = 0; t < T; ++t) {
-        RefineIn nxt = cur;
-        if (t + 1 < T) nxt = refine_load(ft0c, ft1c, d0, d1, v0, t + 1, b, pix, B, T, hw);
-        const float r0u = clamp_pm1(__fadd_rn(cur.d0u, cur.f0u)), r0v = clamp_pm1(__fadd_rn(cur.d0v, cur.f0v));
-        const float r1u = clamp_pm1(__fadd_rn(cur.d1u, cur.f1u)), r1v = clamp_pm1(__fadd_rn(cur.d1v, cur.f1v));
-        const WarpCoord c0 = warp_coord(x, y, r0u, r0v, g), c1 = warp_coord(x, y, r1u, r1v, g);
-        const Frac q0 = frac_of(c0), q1 = frac_of(c1);
-        const float *p0 = patch + patch_offset(c0, tx0, ty0), *p1 = patch + CT * PLANE + patch_offset(c1, tx0, ty0);
-        const float k0 = tm.omt[t] * cur.vis, k1 = tm.t[t] * (1.f - cur.vis);
-        const float inv = 1.f / (k0 + k1);
-        float *out = pred + ((long)b * T + (T - 1 - t)) * CT * hw + pix;
+    if (!q.active) return;
+    auto step = [&](const RefineIn4 &cur, int t) {
+        const float omt = tm.omt[t], tt = tm.t[t];
+        float4 o[CT];
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) {
-            const float *a = p0 + ch * PLANE, *c = p1 + ch * PLANE;
+        for (int j = 0; j < 4; ++j) {
+            const float r0u = clamp_pm1(__fadd_rn(comp(cur.d0u, j), comp(cur.f0u, j)));
+            const float r0v = clamp_pm1(__fadd_rn(comp(cur.d0v, j), comp(cur.f0v, j)));
+            const float r1u = clamp_pm1(__fadd_rn(comp(cur.d1u, j), comp(cur.f1u, j)));
+            const float r1v = clamp_pm1(__fadd_rn(comp(cur.d1v, j), comp(cur.f1v, j)));
+            const WarpCoord c0 = warp_coord(q.x + j, q.y, r0u, r0v, g), c1 = warp_coord(q.x + j, q.y, r1u, r1v, g);
+            const Frac q0 = frac_of(c0), q1 = frac_of(c1);
+            const float *p0 = patch + patch_offset(c0, q.tx0, q.ty0), *p1 = patch + CT * PLANE + patch_offset(c1, q.tx0, q.ty0);
+            const float vis = comp(cur.vis, j);
+            const float k0 = omt * vis, k1 = tt * (1.f - vis);
+            const float inv = 1.f / (k0 + k1);
             // same weights and summation order as sample(): nw*wnw + ne*wne + sw*wsw + se*wse
-            const float a0 = a[0] * (q0.ax * q0.ay) + a[1] * (q0.bx * q0.ay) + a[kSbPitch] * (q0.ax * q0.by) + a[kSbPitch + 1] * (q0.bx * q0.by);
-            const float a1 = c[0] * (q1.ax * q1.ay) + c[1] * (q1.bx * q1.ay) + c[kSbPitch] * (q1.ax * q1.by) + c[kSbPitch + 1] * (q1.bx * q1.by);
-            out[(long)ch * hw] = (k0 * a0 + k1 * a1) * inv;
+            const float w00 = q0.ax * q0.ay, w01 = q0.bx * q0.ay, w02 = q0.ax * q0.by, w03 = q0.bx * q0.by;
+            const float w10 = q1.ax * q1.ay, w11 = q1.bx * q1.ay, w12 = q1.ax * q1.by, w13 = q1.bx * q1.by;
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) {
+                const float *a = p0 + ch * PLANE, *c = p1 + ch * PLANE;
+                const float a0 = a[0] * w00 + a[1] * w01 + a[kQPitch] * w02 + a[kQPitch + 1] * w03;
+                const float a1 = c[0] * w10 + c[1] * w11 + c[kQPitch] * w12 + c[kQPitch + 1] * w13;
+                set_comp(o[ch], j, (k0 * a0 + k1 * a1) * inv);
+            }
         }
-        cur = nxt;
+        float *out = pred + ((long)q.b * T + (T - 1 - t)) * CT * hw + q.pix;
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) *reinterpret_cast<float4 *>(out + (long)ch * hw) = o[ch];
+    };
+    // two steps per trip, the operands of the next step in flight while this one is computed (no register copies)
+    for (int t = 0; t < T; t += 2) {
+        RefineIn4 rb;
+        if (t + 1 < T) rb = refine_load4(ft0c, ft1c, d0, d1, v0, t + 1, q.b, q.pix, B, T, hw);
+        step(ra, t);
+        if (t + 1 < T) {
+            if (t + 2 < T) ra = refine_load4(ft0c, ft1c, d0, d1, v0, t + 2, q.b, q.pix, B, T, hw);
+            step(rb, t + 1);
+        }
     }
 }
 
 template <int CT>
-__global__ void __launch_bounds__(256)
-slomo_refine_blend_tiled_bwd_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
-                                    const float *__restrict__ ft0c, const float *__restrict__ ft1c,
-                                    const float *__restrict__ d0, const float *__restrict__ d1,
-                                    const float *__restrict__ v0, const SlomoTimes tm, const float *__restrict__ gpred,
-                                    float *__restrict__ gft0c, float *__restrict__ gft1c, float *__restrict__ gd0,
-                                    float *__restrict__ gd1, float *__restrict__ gv0, int B, int tiles_x, int tiles_y,
-                                    const WarpGeom g)
+__global__ void __launch_bounds__(kQThreads)
+slomo_refine_blend_quad_bwd_kernel(const float *__restrict__ i0, const float *__restrict__ i1,
+                                   const float *__restrict__ ft0c, const float *__restrict__ ft1c,
+                                   const float *__restrict__ d0, const float *__restrict__ d1,
+                                   const float *__restrict__ v0, const SlomoTimes tm, const float *__restrict__ gpred,
+                                   float *__restrict__ gft0c, float *__restrict__ gft1c, float *__restrict__ gd0,
+                                   float *__restrict__ gd1, float *__restrict__ gv0, int B, int tiles_x, int tiles_y,
+                                   const WarpGeom g)
 {
-    __shared__ float patch[2 * CT * kSbPH * kSbPitch];
-    constexpr int PLANE = kSbPH * kSbPitch;
+    __shared__ float patch[2 * CT * kQPH * kQPitch];
+    constexpr int PLANE = kQPH * kQPitch;
     const int H = g.H, W = g.W, T = tm.T;
     const int hw = H * W;
     const float sx = (float)(W - 1) / (float)W, sy = (float)(H - 1) / (float)H;
-    int tile = blockIdx.x;
-    const int tx0 = (tile % tiles_x) * kSbTW;
-    tile /= tiles_x;
-    const int ty0 = (tile % tiles_y) * kSbTH, b = tile / tiles_y;
-    const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
-    const bool active = x < W && y < H;
-    const int pix = active ? y * W + x : 0;
-    RefineIn cur = refine_load(ft0c, ft1c, d0, d1, v0, 0, b, pix, B, T, hw);
-    refine_stage_patch<CT>(patch, i0, i1, b, tx0, ty0, H, W);
+    const QuadGeom q = quad_geom(tiles_x, tiles_y, H, W);
+    RefineIn4 cur = refine_load4(ft0c, ft1c, d0, d1, v0, 0, q.b, q.pix, B, T, hw);
+    refine_stage_patch<CT>(patch, i0, i1, q.b, q.tx0, q.ty0, H, W);
     __syncthreads();
-    if (!active) return;
+    if (!q.active) return;
     for (int t = 0; t < T; ++t) {
-        RefineIn nxt = cur;
-        if (t + 1 < T) nxt = refine_load(ft0c, ft1c, d0, d1, v0, t + 1, b, pix, B, T, hw);
-        const long nb = (long)t * B + b;
-        const long du = nb * 2 * hw + pix, dv = du + hw;
-        const long slot = (long)b * T + (T - 1 - t);
-        const long fu = slot * 2 * hw + pix, fv = fu + hw;
-        const float s0u = __fadd_rn(cur.d0u, cur.f0u), s0v = __fadd_rn(cur.d0v, cur.f0v);
-        const float s1u = __fadd_rn(cur.d1u, cur.f1u), s1v = __fadd_rn(cur.d1v, cur.f1v);
-        const WarpCoord c0 = warp_coord(x, y, clamp_pm1(s0u), clamp_pm1(s0v), g);
-        const WarpCoord c1 = warp_coord(x, y, clamp_pm1(s1u), clamp_pm1(s1v), g);
-        const Frac q0 = frac_of(c0), q1 = frac_of(c1);
-        const float *p0 = patch + patch_offset(c0, tx0, ty0), *p1 = patch + CT * PLANE + patch_offset(c1, tx0, ty0);
-        const float omt = tm.omt[t], tt = tm.t[t];
-        const float k0 = omt * cur.vis, k1 = tt * (1.f - cur.vis);
-        const float inv = 1.f / (k0 + k1);
-        const float *go = gpred + slot * CT * hw + pix;
-        float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, gv = 0.f;
+        const long nb = (long)t * B + q.b;
+        const long du = nb * 2 * hw + q.pix, dv = du + hw;
+        const long slot = (long)q.b * T + (T - 1 - t);
+        const long fu = slot * 2 * hw + q.pix, fv = fu + hw;
+        const float *go = gpred + slot * CT * hw + q.pix;
+        float4 gch[CT];
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) {
-            const float gch = ld_stream(go + (long)ch * hw);
-            const float *a = p0 + ch * PLANE, *c = p1 + ch * PLANE;
-            const float nw0 = a[0], ne0 = a[1], sw0 = a[kSbPitch], se0 = a[kSbPitch + 1];
-            const float nw1 = c[0], ne1 = c[1], sw1 = c[kSbPitch], se1 = c[kSbPitch + 1];
-            const float a0 = nw0 * (q0.ax * q0.ay) + ne0 * (q0.bx * q0.ay) + sw0 * (q0.ax * q0.by) + se0 * (q0.bx * q0.by);
-            const float a1 = nw1 * (q1.ax * q1.ay) + ne1 * (q1.bx * q1.ay) + sw1 * (q1.ax * q1.by) + se1 * (q1.bx * q1.by);
-            const float ga0 = gch * k0 * inv, ga1 = gch * k1 * inv;
-            gx0 += ga0 * ((ne0 - nw0) * q0.ay + (se0 - sw0) * q0.by);
-            gy0 += ga0 * ((sw0 - nw0) * q0.ax + (se0 - ne0) * q0.bx);
-            gx1 += ga1 * ((ne1 - nw1) * q1.ay + (se1 - sw1) * q1.by);
-            gy1 += ga1 * ((sw1 - nw1) * q1.ax + (se1 - ne1) * q1.bx);
-            const float o = (k0 * a0 + k1 * a1) * inv;
-            gv += gch * ((omt * a0 - tt * a1) - o * (omt - tt)) * inv;
+        for (int ch = 0; ch < CT; ++ch) gch[ch] = ld_stream4(reinterpret_cast<const float4 *>(go + (long)ch * hw));
+        RefineIn4 nxt = cur;
+        if (t + 1 < T) nxt = refine_load4(ft0c, ft1c, d0, d1, v0, t + 1, q.b, q.pix, B, T, hw);
+        const float omt = tm.omt[t], tt = tm.t[t];
+        float4 o0u, o0v, o1u, o1v, ov;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float s0u = __fadd_rn(comp(cur.d0u, j), comp(cur.f0u, j)), s0v = __fadd_rn(comp(cur.d0v, j), comp(cur.f0v, j));
+            const float s1u = __fadd_rn(comp(cur.d1u, j), comp(cur.f1u, j)), s1v = __fadd_rn(comp(cur.d1v, j), comp(cur.f1v, j));
+            const WarpCoord c0 = warp_coord(q.x + j, q.y, clamp_pm1(s0u), clamp_pm1(s0v), g);
+            const WarpCoord c1 = warp_coord(q.x + j, q.y, clamp_pm1(s1u), clamp_pm1(s1v), g);
+            const Frac q0 = frac_of(c0), q1 = frac_of(c1);
+            const float *p0 = patch + patch_offset(c0, q.tx0, q.ty0), *p1 = patch + CT * PLANE + patch_offset(c1, q.tx0, q.ty0);
+            const float vis = comp(cur.vis, j);
+            const float k0 = omt * vis, k1 = tt * (1.f - vis);
+            const float inv = 1.f / (k0 + k1);
+            float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, gv = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) {
+                const float gc = comp(gch[ch], j);
+                const float *a = p0 + ch * PLANE, *c = p1 + ch * PLANE;
+                const float nw0 = a[0], ne0 = a[1], sw0 = a[kQPitch], se0 = a[kQPitch + 1];
+                const float nw1 = c[0], ne1 = c[1], sw1 = c[kQPitch], se1 = c[kQPitch + 1];
+                const float a0 = nw0 * (q0.ax * q0.ay) + ne0 * (q0.bx * q0.ay) + sw0 * (q0.ax * q0.by) + se0 * (q0.bx * q0.by);
+                const float a1 = nw1 * (q1.ax * q1.ay) + ne1 * (q1.bx * q1.ay) + sw1 * (q1.ax * q1.by) + se1 * (q1.bx * q1.by);
+                const float ga0 = gc * k0 * inv, ga1 = gc * k1 * inv;
+                gx0 += ga0 * ((ne0 - nw0) * q0.ay + (se0 - sw0) * q0.by);
+                gy0 += ga0 * ((sw0 - nw0) * q0.ax + (se0 - ne0) * q0.bx);
+                gx1 += ga1 * ((ne1 - nw1) * q1.ay + (se1 - sw1) * q1.by);
+                gy1 += ga1 * ((sw1 - nw1) * q1.ax + (se1 - ne1) * q1.bx);
+                const float o = (k0 * a0 + k1 * a1) * inv;
+                gv += gc * ((omt * a0 - tt * a1) - o * (omt - tt)) * inv;
+            }
+            set_comp(o0u, j, (s0u >= -1.f && s0u <= 1.f) ? gx0 * sx : 0.f);
+            set_comp(o0v, j, (s0v >= -1.f && s0v <= 1.f) ? gy0 * sy : 0.f);
+            set_comp(o1u, j, (s1u >= -1.f && s1u <= 1.f) ? gx1 * sx : 0.f);
+            set_comp(o1v, j, (s1v >= -1.f && s1v <= 1.f) ? gy1 * sy : 0.f);
+            set_comp(ov, j, gv);
         }
-        const float r0u = (s0u >= -1.f && s0u <= 1.f) ? gx0 * sx : 0.f, r0v = (s0v >= -1.f && s0v <= 1.f) ? gy0 * sy : 0.f;
-        const float r1u = (s1u >= -1.f && s1u <= 1.f) ? gx1 * sx : 0.f, r1v = (s1v >= -1.f && s1v <= 1.f) ? gy1 * sy : 0.f;
-        gd0[du] = r0u; gd0[dv] = r0v;
-        gd1[du] = r1u; gd1[dv] = r1v;
-        gft0c[fu] = r0u; gft0c[fv] = r0v;
-        gft1c[fu] = r1u; gft1c[fv] = r1v;
-        gv0[nb * hw + pix] = gv;
+        auto S = [](float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; };
+        S(gd0 + du, o0u); S(gd0 + dv, o0v);
+        S(gd1 + du, o1u); S(gd1 + dv, o1v);
+        S(gft0c + fu, o0u); S(gft0c + fv, o0v);
+        S(gft1c + fu, o1u); S(gft1c + fv, o1v);
+        S(gv0 + nb * hw + q.pix, ov);
         cur = nxt;
     }
 }
@@ -593,16 +690,18 @@ extern "C" int slomo_refine_blend_batched_forward_b200(const float *i0, const fl
     const WarpGeom g = warp_geom(H, W);
     const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    const int tiles_x = ceil_div(W, kSbTW), tiles_y = ceil_div(H, kSbTH);
-    if ((C == 1 || C == 3) && fits_int31((long long)B * tiles_x * tiles_y)) {   // frames staged in shared memory
+    const int tiles_x = ceil_div(W, kQW), tiles_y = ceil_div(H, kQH);
+    const bool quads_aligned = (((uintptr_t)f_t0_collector | (uintptr_t)f_t1_collector | (uintptr_t)d_t0 | (uintptr_t)d_t1 |
+                                 (uintptr_t)v_t0 | (uintptr_t)pred) & 15) == 0;
+    if ((C == 1 || C == 3) && W % 4 == 0 && quads_aligned && fits_int31((long long)B * tiles_x * tiles_y)) {   // four pixels per thread
         const unsigned grid = (unsigned)((long)B * tiles_x * tiles_y);
         if (C == 3)
-            slomo_refine_blend_tiled_kernel<3><<<grid, 256, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+            slomo_refine_blend_quad_kernel<3><<<grid, kQThreads, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                                                                      pred, B, tiles_x, tiles_y, g);
         else
-            slomo_refine_blend_tiled_kernel<1><<<grid, 256, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+            slomo_refine_blend_quad_kernel<1><<<grid, kQThreads, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                                                                      pred, B, tiles_x, tiles_y, g);
-        return check_launch("slomo_refine_blend_tiled_kernel");
+        return check_launch("slomo_refine_blend_quad_kernel");
     }
     TAI_SLOMO_DISPATCH(slomo_refine_blend_t_kernel, items, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                        pred, B, C, g);
@@ -626,18 +725,21 @@ extern "C" int slomo_refine_blend_batched_backward_b200(const float *i0, const f
     const WarpGeom g = warp_geom(H, W);
     const long items = (long)B * H * W;
     const SlomoTimes tm = slomo_times(T);
-    const int tiles_x = ceil_div(W, kSbTW), tiles_y = ceil_div(H, kSbTH);
-    if ((C == 1 || C == 3) && fits_int31((long long)B * tiles_x * tiles_y)) {
+    const int tiles_x = ceil_div(W, kQW), tiles_y = ceil_div(H, kQH);
+    const bool quads_aligned = (((uintptr_t)f_t0_collector | (uintptr_t)f_t1_collector | (uintptr_t)d_t0 | (uintptr_t)d_t1 |
+                                 (uintptr_t)v_t0 | (uintptr_t)g_pred | (uintptr_t)g_f_t0_collector | (uintptr_t)g_f_t1_collector |
+                                 (uintptr_t)g_d_t0 | (uintptr_t)g_d_t1 | (uintptr_t)g_v_t0) & 15) == 0;
+    if ((C == 1 || C == 3) && W % 4 == 0 && quads_aligned && fits_int31((long long)B * tiles_x * tiles_y)) {
         const unsigned grid = (unsigned)((long)B * tiles_x * tiles_y);
         if (C == 3)
-            slomo_refine_blend_tiled_bwd_kernel<3><<<grid, 256, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+            slomo_refine_blend_quad_bwd_kernel<3><<<grid, kQThreads, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                                                                          g_pred, g_f_t0_collector, g_f_t1_collector, g_d_t0,
                                                                          g_d_t1, g_v_t0, B, tiles_x, tiles_y, g);
         else
-            slomo_refine_blend_tiled_bwd_kernel<1><<<grid, 256, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
+            slomo_refine_blend_quad_bwd_kernel<1><<<grid, kQThreads, 0, st>>>(i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0, tm,
                                                                          g_pred, g_f_t0_collector, g_f_t1_collector, g_d_t0,
                                                                          g_d_t1, g_v_t0, B, tiles_x, tiles_y, g);
-        return check_launch("slomo_refine_blend_tiled_bwd_kernel");
+        return check_launch("slomo_refine_blend_quad_bwd_kernel");
     }
     TAI_SLOMO_DISPATCH(slomo_refine_blend_t_bwd_kernel, items, st, i0, i1, f_t0_collector, f_t1_collector, d_t0, d_t1, v_t0,
                        tm, g_pred, g_f_t0_collector, g_f_t1_collector, g_d_t0, g_d_t1, g_v_t0, B, C, g);

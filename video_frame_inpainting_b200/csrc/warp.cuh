@@ -65,8 +65,10 @@ __device__ __forceinline__ float div_by_size(float a, float b, float y)
 __device__ __forceinline__ float warp_axis(float pos, float flow, float size, float rsize)
 {
     const float X = __fadd_rn(pos, flow);
-    const float g = __fmul_rn(2.f, __fsub_rn(div_by_size(X, size, rsize), 0.5f));
-    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), size - 1.f);   // (g + 1) / 2: halving is exact
+    // g = 2 (X/size - 0.5) and (g + 1) / 2: doubling and halving are exact and commute with rounding, so
+    // RN(RN(2 s) + 1) / 2 == RN(s + 0.5) bit for bit (s = RN(X/size - 0.5); no overflow or underflow here)
+    const float s = __fsub_rn(div_by_size(X, size, rsize), 0.5f);
+    return __fmul_rn(__fadd_rn(s, 0.5f), size - 1.f);
 }
 
 struct WarpGeom {
