@@ -30,7 +30,7 @@ sepconv_bwd_vh_kernel(const BwdParams p)
     constexpr int NT = 32 * WX * WY;
     constexpr int TILE_W = WX * BNX, TILE_H = WY * BP;
     constexpr int PITCH = TILE_W + 4 * J;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(1024) float smem[];
 
     const int ks = p.ks, Ho = p.Ho, Wo = p.Wo;
     const int Hi = Ho + ks - 1, Wi = Wo + ks - 1;
@@ -430,7 +430,8 @@ static int launch_vh_v3(const BwdParams &p0, cudaStream_t st)
     using Cfg = VhV3Cfg<KS>;
     BwdParams p = p0;
     VhV3Maps maps;
-    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+    static_assert(Cfg::TILE_W == 32, "the swizzled H box is one 128-byte line per (row, tap)");
+    if (!make_kernel_map_tmap_swz(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_H, KS) ||
         !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
         return 1;
     p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
@@ -506,7 +507,8 @@ static int launch_gi_v4(const BwdParams &p0, cudaStream_t st)
     using Cfg = GiV4Cfg<KS>;
     BwdParams p = p0;
     GiV4Maps maps;
-    if (!make_kernel_map_tmap(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+    static_assert(Cfg::TILE_W == 32, "the swizzled H box is one 128-byte line per (row, tap)");
+    if (!make_kernel_map_tmap_swz(&maps.h, p.hor, p.B, KS, p.Ho, p.Wo, Cfg::TILE_H, KS) ||
         !make_kernel_map_tmap(&maps.v, p.ver, p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
         return 1;
     p.ntx = ceil_div(p.Wo, Cfg::TILE_W);

@@ -69,7 +69,7 @@ struct GiV4Cfg {
 };
 
 struct GiV4Maps {
-    CUtensorMap h;  // box {32, 8, KS, 1}
+    CUtensorMap h;  // box {32, KS, 8, 1}, 128-byte swizzle (make_kernel_map_tmap_swz)
     CUtensorMap v;  // box {32, 8, CH_TAPS, 1}
 };
 
@@ -139,7 +139,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
 {
     using Cfg = GiV4Cfg<KS>;
     constexpr int JP = Cfg::JP, E = Cfg::E, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(1024) float smem[];
     float *slab = smem;
     float *win = smem + Cfg::SLAB_FLOATS;                       // [4 warps][2 groups][GROWS][WCOLS]
     float *tsb = win + Cfg::WX * Cfg::WIN_FLOATS;               // [4 warps][64][4]
@@ -163,8 +163,11 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
 #pragma unroll
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
+        if ((__cvta_generic_to_shared(slab) & 1023) != 0) __trap();  // the swizzle pattern is tied to 1024-byte blocks
     }
     for (int i = threadIdx.x; i < Cfg::WX * Cfg::TS_FLOATS; i += Cfg::NT) tsb[i] = 0.f;  // unwritten slots stay zero
+    int swz[8];
+    swz_table(warp * FNX + cx, ch, swz);
     __syncthreads();
     uint32_t parity = 0;
 
@@ -180,7 +183,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
         if (threadIdx.x == 0) {
             fence_proxy_async();
             mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
-            tma_load_4d(slab, &maps.h, &bars[0], x0, y0, 0, b);  // out-of-range rows / columns arrive as zeros
+            tma_load_4d(slab, &maps.h, &bars[0], x0, 0, y0, b);  // out-of-range rows / columns arrive as zeros
         }
         float go[FP];
         if (FOLD) {
@@ -193,16 +196,15 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
         // place and rotate the even ones up by two (see the pair exchange in gi_row_v4)
         float h[FP][JP];
         {
-            const float *hs = slab + ch * Cfg::VROW + warp * FNX + cx;
 #pragma unroll
             for (int s = 0; s < JP; ++s) {
                 const int kh = (s & 1) ? s : (s == 0 ? JP - 1 : s - 2);
-                const int k = hi ? kh : s;
+                const int k = hi ? kh : s;     // k and s have the same parity: the swizzle slot is a compile-time index
                 const bool ok = ch + 4 * k < KS;
-                const float *hk = hs + (4 * k) * Cfg::VROW;
+                const float *hk = slab + (4 * k) * 32;
 #pragma unroll
                 for (int r = 0; r < FP; ++r) {
-                    const float hv = ok ? hk[r * TILE_W] : 0.f;
+                    const float hv = ok ? hk[r * KS * 32 + swz[(r * KS + 4 * s) & 7]] : 0.f;
                     h[r][s] = FOLD ? hv * go[r] : hv;
                 }
             }
@@ -220,7 +222,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
                 const int nx0 = (n % p.ntx) * TILE_W;
                 n /= p.ntx;
                 const int ny0 = (n % p.nty) * TILE_H, nb = n / p.nty;
-                tma_prefetch_l2_4d(&maps.h, nx0, ny0, 0, nb);
+                tma_prefetch_l2_4d(&maps.h, nx0, 0, ny0, nb);
 #pragma unroll
                 for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
             }

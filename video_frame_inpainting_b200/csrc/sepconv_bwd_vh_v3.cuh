@@ -58,7 +58,7 @@ struct VhV3Cfg {
 };
 
 struct VhV3Maps {
-    CUtensorMap h;  // box {32, 4, KS, 1}
+    CUtensorMap h;  // box {32, KS, 4, 1}, 128-byte swizzle (make_kernel_map_tmap_swz)
     CUtensorMap v;  // box {32, 4, CH_TAPS, 1}
 };
 
@@ -113,10 +113,10 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
     using Cfg = VhV3Cfg<KS>;
     constexpr int J = Cfg::J, PITCH = Cfg::PITCH, ROWS = Cfg::ROWS, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
     constexpr int CSTRIDE = ROWS * PITCH;
-    extern __shared__ __align__(128) float smem[];
-    float *slab = smem;                                  // V chunks of the current tile
-    float *hslab = smem + Cfg::SLAB_FLOATS;              // H box of the current tile, then of the next one
-    float *is = hslab + Cfg::HSLAB_FLOATS;
+    extern __shared__ __align__(1024) float smem[];
+    float *hslab = smem;                                 // H box of the current tile, then of the next one (swizzled: 1024-byte aligned)
+    float *slab = smem + Cfg::HSLAB_FLOATS;              // V chunks of the current tile
+    float *is = slab + Cfg::SLAB_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(is + CG * CSTRIDE);
 
     const int Ho = p.Ho, Wo = p.Wo;
@@ -145,15 +145,18 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
 #pragma unroll
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
+        if ((__cvta_generic_to_shared(hslab) & 1023) != 0) __trap();  // the swizzle pattern is tied to 1024-byte blocks
         if (t_lo < t_hi) {   // H box of this CTA's first tile
             int fx, fy, fb;
             tile_origin(t_lo, fx, fy, fb);
             mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
-            tma_load_4d(hslab, &maps.h, &bars[0], fx, fy, 0, fb);
+            tma_load_4d(hslab, &maps.h, &bars[0], fx, 0, fy, fb);
         }
     }
     __syncthreads();
     uint32_t parity = 0;
+    int swz[8];
+    swz_table(warp * FNX + cx, ch, swz);
     int rbase = 0;                          // ring row that holds halo row 0 of the current tile
     int px0 = -1, py0 = -1, pb = -1;        // origin of the previous tile
 
@@ -246,12 +249,11 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
         mbar_wait(&bars[0], parity);
         float h[BP][J], a[BP][J];
         {
-            const float *hs = hslab + ch * Cfg::VROW + warp * FNX + cx;
 #pragma unroll
             for (int jj = 0; jj < J; ++jj)
 #pragma unroll
                 for (int r = 0; r < BP; ++r) {
-                    h[r][jj] = (ch + 4 * jj < KS) ? hs[(4 * jj) * Cfg::VROW + r * TILE_W] : 0.f;
+                    h[r][jj] = (ch + 4 * jj < KS) ? hslab[(r * KS + 4 * jj) * 32 + swz[(r * KS + 4 * jj) & 7]] : 0.f;
                     if (CG == 1) h[r][jj] *= go[0][r];
                     a[r][jj] = 0.f;
                 }
@@ -263,7 +265,7 @@ sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams 
             tile_origin(tile + 1, nx0, ny0, nb);
             fence_proxy_async();
             mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
-            tma_load_4d(hslab, &maps.h, &bars[0], nx0, ny0, 0, nb);
+            tma_load_4d(hslab, &maps.h, &bars[0], nx0, 0, ny0, nb);
 #pragma unroll
             for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v, nx0, ny0, q * Cfg::CH_TAPS, nb);
         }

@@ -63,7 +63,7 @@ sepconv_fwd_kernel(const FwdParams p)
     constexpr int NT = 32 * WX * WY;
     constexpr int TILE_W = WX * FNX, TILE_H = WY * FP;
     constexpr int PITCH = TILE_W + 4 * J;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(1024) float smem[];
 
     const int ks = p.ks, Ho = p.Ho, Wo = p.Wo;
     const int Hi = Ho + ks - 1, Wi = Wo + ks - 1;
@@ -284,7 +284,8 @@ static int launch_fwd_v3(const FwdParams &p0, cudaStream_t st)
     FwdParams p = p0;
     FwdV3Maps maps;
     for (int s = 0; s < (DUAL ? 2 : 1); ++s) {
-        if (!make_kernel_map_tmap(&maps.h[s], p.hor[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+        static_assert(Cfg::TILE_W == 32, "the swizzled H box is one 128-byte line per (row, tap)");
+        if (!make_kernel_map_tmap_swz(&maps.h[s], p.hor[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_H, KS) ||
             !make_kernel_map_tmap(&maps.v[s], p.ver[s], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS))
             return 1;
     }

@@ -65,7 +65,7 @@ struct FwdV3Cfg {
 };
 
 struct FwdV3Maps {
-    CUtensorMap h[2];  // box {32, 8, KS, 1}
+    CUtensorMap h[2];  // box {32, KS, 8, 1}, 128-byte swizzle (make_kernel_map_tmap_swz)
     CUtensorMap v[2];  // box {32, 8, CH_TAPS, 1}
 };
 
@@ -106,8 +106,8 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
     constexpr int J = Cfg::J, PITCH = Cfg::PITCH, ROWS = Cfg::ROWS, TILE_W = Cfg::TILE_W, TILE_H = Cfg::TILE_H;
     constexpr int CSTRIDE = ROWS * PITCH;
     constexpr int NS = DUAL ? 2 : 1;
-    extern __shared__ __align__(128) float smem[];
-    float *slab = smem;                       // [taps][TILE_H][TILE_W], written by TMA only
+    extern __shared__ __align__(1024) float smem[];
+    float *slab = smem;                       // H: [TILE_H][taps][TILE_W] swizzled, V: [taps][TILE_H][TILE_W]; written by TMA only
     float *is = smem + Cfg::SLAB_FLOATS;      // [CG][ROWS][PITCH]
     uint64_t *bars = reinterpret_cast<uint64_t *>(is + CG * CSTRIDE);  // [0]: H box, [1..3]: V chunks
 
@@ -119,12 +119,15 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
     const int ntiles = p.B * p.nty * p.ntx;
 
     if (threadIdx.x == 0) {
+        if ((__cvta_generic_to_shared(slab) & 1023) != 0) __trap();  // the swizzle pattern is tied to 1024-byte blocks
 #pragma unroll
         for (int i = 0; i < Cfg::NBAR; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
     uint32_t parity = 0;  // every barrier completes exactly once per (tile, stream, channel group)
+    int swz[8];
+    swz_table(warp * FNX + cx, ch, swz);
 #ifdef TAI_LAB_TIMING
     long long lab_t_ = clock64();
 #endif
@@ -150,7 +153,7 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                 if (threadIdx.x == 0) {
                     fence_proxy_async();  // generic-proxy reads of the slab (previous sweep) precede the refill
                     mbar_expect_tx(&bars[0], KS * Cfg::VROW * 4);
-                    tma_load_4d(slab, &maps.h[s], &bars[0], x0, y0, 0, b);
+                    tma_load_4d(slab, &maps.h[s], &bars[0], x0, 0, y0, b);
                 }
                 {
                     const float *__restrict__ in = p.in[s];
@@ -205,12 +208,11 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                 LAB_T(1);
                 float h[FP][J];
                 {
-                    const float *hs = slab + ch * Cfg::VROW + warp * FNX + cx;
 #pragma unroll
                     for (int jj = 0; jj < J; ++jj)
 #pragma unroll
                         for (int r = 0; r < FP; ++r)
-                            h[r][jj] = (ch + 4 * jj < KS) ? hs[(4 * jj) * Cfg::VROW + r * TILE_W] : 0.f;
+                            h[r][jj] = (ch + 4 * jj < KS) ? slab[(r * KS + 4 * jj) * 32 + swz[(r * KS + 4 * jj) & 7]] : 0.f;
                 }
                 __syncthreads();  // H is in registers everywhere; the halo is complete
                 LAB_T(2);
@@ -228,7 +230,7 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                     // early put 8 boxes (209 KB) per CTA in flight: 93 MB for 444 CTAs, which the 126 MB L2 evicted
                     // before use -- ncu r01 read 3.24 GB from DRAM for 2.19 GB of maps.
                     if (DUAL && s == 0) {
-                        tma_prefetch_l2_4d(&maps.h[1], x0, y0, 0, b);
+                        tma_prefetch_l2_4d(&maps.h[1], x0, 0, y0, b);
 #pragma unroll
                         for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v[1], x0, y0, q * Cfg::CH_TAPS, b);
                     } else if (c0 + CG >= p.C && tile + (int)gridDim.x < ntiles) {
@@ -238,7 +240,7 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                         const int nty_ = n % p.nty;
                         const int nb = n / p.nty;
                         const int nx0 = max(0, min(ntx_ * TILE_W, Wo - TILE_W)), ny0 = min(nty_ * TILE_H, Ho - TILE_H);
-                        tma_prefetch_l2_4d(&maps.h[0], nx0, ny0, 0, nb);
+                        tma_prefetch_l2_4d(&maps.h[0], nx0, 0, ny0, nb);
 #pragma unroll
                         for (int q = 0; q < Cfg::NCHUNK; ++q) tma_prefetch_l2_4d(&maps.v[0], nx0, ny0, q * Cfg::CH_TAPS, nb);
                     }

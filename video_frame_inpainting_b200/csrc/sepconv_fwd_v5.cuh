@@ -124,7 +124,7 @@ sepconv_fwd_v5_kernel(const __grid_constant__ FwdV5Maps maps, const FwdParams p,
     constexpr int NS = DUAL ? 2 : 1;
     constexpr int NK = (PITCH + 31) / 32;
     constexpr uint32_t CHUNK_BYTES = Cfg::CHUNK_FLOATS * 4;
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(1024) float smem[];
     float *slab = smem;                       // [NCH][CT][TILE_H][TILE_W], written by TMA only
     float *is = smem + Cfg::SLAB_FLOATS;      // [CG][ROWS (ring)][PITCH] + TAIL
     uint64_t *full = reinterpret_cast<uint64_t *>(is + CG * CSTRIDE + Cfg::TAIL);

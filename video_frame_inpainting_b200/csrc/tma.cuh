@@ -151,4 +151,32 @@ inline bool make_kernel_map_tmap(CUtensorMap *tm, const float *base, int B, int 
     return r == CUDA_SUCCESS;
 }
 
+// The same tensor with the tap index as the SECOND box dimension and the 128-byte swizzle: shared-memory image
+// [row][tap][32 cols], one 128-byte line per (row, tap), 16-byte chunk c of line rho stored at chunk c ^ (rho & 7)
+// (the destination must be 1024-byte aligned).  Why: in the dense [tap][row][col] image every stride is a multiple of
+// 32 banks, so the four tap groups of a warp (which read four different taps of the same 8 columns) collide 4-way when
+// the taps are copied to registers; here consecutive taps get different XOR masks and the copy is 2-way.
+inline bool make_kernel_map_tmap_swz(CUtensorMap *tm, const float *base, int B, int ks, int Ho, int Wo, int bh, int btaps)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    if ((Wo % 4) != 0 || (((uintptr_t)base) & 15) != 0) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)Wo, (cuuint64_t)ks, (cuuint64_t)Ho, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Ho * Wo * 4, (cuuint64_t)Wo * 4, (cuuint64_t)ks * Ho * Wo * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)btaps, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Per-lane offsets into a swizzled [row][tap][32] box for the lane's column `col` and tap group `ch`:
+// element (row r, tap ch + 4 jj) lives at  (r * KS + 4 * jj) * 32 + ch * 32 + tbl[(r * KS + 4 * jj) & 7].
+__device__ __forceinline__ void swz_table(int col, int ch, int (&tbl)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tbl[k] = ch * 32 + ((((col >> 2) ^ ((k + ch) & 7)) << 2) | (col & 3));
+}
+
 }  // namespace tai
