@@ -58,7 +58,10 @@ struct GiV4Cfg {
     static constexpr int DCOLS = TILE_W + KS - 1;    // destination columns per CTA
     static constexpr int GROWS = 8;                  // destination rows per flush group
     static constexpr int NGROUPS = (DROWS + GROWS - 1) / GROWS;
-    static constexpr int WIN_FLOATS = 2 * GROWS * WCOLS;  // per warp: two groups (one being written, one being flushed)
+    static constexpr int WPITCH = (WCOLS + 3) / 4 * 4;    // window row pitch: whole 16-byte column quads (the pad stays zero)
+    static constexpr int WQUADS = WPITCH / 4;             // column quads per warp window row
+    static constexpr int DQUADS = (DCOLS + 3) / 4;        // column quads per CTA row
+    static constexpr int WIN_FLOATS = 2 * GROWS * WPITCH; // per warp: two groups (one being written, one being flushed)
     static constexpr int TS_FLOATS = 4 * 64;              // per warp: [destination column 0..63][contributor ch]
     static constexpr int NBAR = 1 + NCHUNK;
     static constexpr size_t smem_bytes() { return (size_t)(SLAB_FLOATS + WX * (WIN_FLOATS + TS_FLOATS)) * 4 + 8 * NBAR; }
@@ -66,6 +69,7 @@ struct GiV4Cfg {
     static_assert(WCOLS <= 64, "two destination columns per lane");
     static_assert(FNX + 2 + 8 * (E - 1) < 64, "staging buffer holds destination columns 0..63");
     static_assert((SLAB_FLOATS % 4) == 0 && (WIN_FLOATS % 4) == 0, "16-byte alignment of the staging buffer");
+    static_assert(FNX % 4 == 0, "a column quad of the CTA row is a column quad of every warp window");
 };
 
 struct GiV4Maps {
@@ -166,6 +170,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
         if ((__cvta_generic_to_shared(slab) & 1023) != 0) __trap();  // the swizzle pattern is tied to 1024-byte blocks
     }
     for (int i = threadIdx.x; i < Cfg::WX * Cfg::TS_FLOATS; i += Cfg::NT) tsb[i] = 0.f;  // unwritten slots stay zero
+    for (int i = threadIdx.x; i < Cfg::WX * Cfg::WIN_FLOATS; i += Cfg::NT) win[i] = 0.f;  // so do the pad columns of the windows
     int swz[8];
     swz_table(warp * FNX + cx, ch, swz);
     __syncthreads();
@@ -229,7 +234,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
         }
         const float *vrow = slab + warp * FNX + cx;
         auto wrow = [&](int yy) {  // this warp's window row of destination row yy (rolling: group parity, row in group)
-            return mywin + (((yy >> 3) & 1) * Cfg::GROWS + (yy & 7)) * Cfg::WCOLS;
+            return mywin + (((yy >> 3) & 1) * Cfg::GROWS + (yy & 7)) * Cfg::WPITCH;
         };
 
         const int nch = FOLD ? 1 : p.C;
@@ -239,22 +244,32 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
             // point of the sweep; the barrier also separates this group's buffer from its reuse two groups later.
             auto flush = [&](int g) {
                 __syncthreads();
-                // a thread per destination column, rows in turn.  (Dealing the 8 x 82 elements round-robin to all
-                // 128 threads was measured slower: 0.556 vs 0.538 ms at B = 160 -- the index division and the
-                // row-crossing atomics cost more than the idle fourth warp.)
-                const int D = threadIdx.x;
-                if (D < Cfg::DCOLS && x0 + D < Wi) {
-                    const float *wb = win + (g & 1) * Cfg::GROWS * Cfg::WCOLS;
-                    const int nrow = min(Cfg::GROWS, Cfg::DROWS - g * Cfg::GROWS);
-                    for (int r = 0; r < nrow; ++r) {
-                        float sum = 0.f;
+                // All 128 threads: work item = (row of the group, quad of 4 destination columns).  Warp w's window
+                // holds destination columns 8w .. 8w+57 at index D - 8w, so a CTA quad Q is quad Q - 2w of window w:
+                // one 128-bit load per contributing warp, no per-element index arithmetic.  (First version: a thread
+                // per destination column, 8 rows x up to 4 scalar loads each, 82 of 128 threads busy: the flush was
+                // 17 % of the kernel in an ablation build.)
+                const float *wb = win + (g & 1) * Cfg::GROWS * Cfg::WPITCH;
+                const int nrow = min(Cfg::GROWS, Cfg::DROWS - g * Cfg::GROWS);
+                for (int item = threadIdx.x; item < nrow * Cfg::DQUADS; item += Cfg::NT) {
+                    const int r = item / Cfg::DQUADS, Q = item - r * Cfg::DQUADS;
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int w = 0; w < Cfg::WX; ++w) {
-                            const int dc = D - w * FNX;
-                            if (dc >= 0 && dc < Cfg::WCOLS) sum += wb[w * Cfg::WIN_FLOATS + r * Cfg::WCOLS + dc];
+                    for (int w = 0; w < Cfg::WX; ++w) {
+                        const int q = Q - w * (FNX / 4);
+                        if (q >= 0 && q < Cfg::WQUADS) {
+                            const float4 v = *reinterpret_cast<const float4 *>(wb + w * Cfg::WIN_FLOATS + r * Cfg::WPITCH + 4 * q);
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                         }
-                        const int yy = g * Cfg::GROWS + r;
-                        if (y0 + yy < Hi) atomicAdd(gdst + (long)yy * Wi + D, sum);
+                    }
+                    const int yy = g * Cfg::GROWS + r;
+                    if (y0 + yy < Hi) {
+                        float *d = gdst + (long)yy * Wi + 4 * Q;
+                        const int D = 4 * Q, lim = min(Cfg::DCOLS, Wi - x0);
+                        if (D < lim) atomicAdd(d, sum.x);
+                        if (D + 1 < lim) atomicAdd(d + 1, sum.y);
+                        if (D + 2 < lim) atomicAdd(d + 2, sum.z);
+                        if (D + 3 < lim) atomicAdd(d + 3, sum.w);
                     }
                 }
             };
