@@ -77,6 +77,13 @@ struct GiV4Maps {
     CUtensorMap v;  // box {32, 8, CH_TAPS, 1}
 };
 
+// Two adjacent floats added to global memory with one reduction (sm_90+; 8-byte aligned address).  The flush is bound
+// by the SM's rate of global reductions per lane, not by bytes: pairs halve it.
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
 // The staged row: destination column d of the warp is the sum of the four floats at ts[4d..4d+3].
 struct GiV4Diag {
     float4 a, b;  // destination columns lane and lane + 32
@@ -155,6 +162,7 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
     const int cx = lane & 7, ch = lane >> 3;
     const bool hi = cx >= 4;
     const int ntiles = p.B * p.nty * p.ntx;
+    const bool pairs = (Wi % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.gin) & 7) == 0);   // 64-bit reductions possible
     const float *ts = tsb + warp * Cfg::TS_FLOATS;
     // after the pair exchange value q of a lane belongs to destination column cx + ch + 8q (lanes cx < 4) or
     // cx + ch + 8((q-1) mod E) (lanes cx >= 4); contributor slot = ch
@@ -266,10 +274,15 @@ sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p
                     if (y0 + yy < Hi) {
                         float *d = gdst + (long)yy * Wi + 4 * Q;
                         const int D = 4 * Q, lim = min(Cfg::DCOLS, Wi - x0);
-                        if (D < lim) atomicAdd(d, sum.x);
-                        if (D + 1 < lim) atomicAdd(d + 1, sum.y);
-                        if (D + 2 < lim) atomicAdd(d + 2, sum.z);
-                        if (D + 3 < lim) atomicAdd(d + 3, sum.w);
+                        if (pairs) {   // Wi, x0 and the quad offset are even: a pair never straddles the row limit
+                            if (D < lim) red_add_v2(d, sum.x, sum.y);
+                            if (D + 2 < lim) red_add_v2(d + 2, sum.z, sum.w);
+                        } else {
+                            if (D < lim) atomicAdd(d, sum.x);
+                            if (D + 1 < lim) atomicAdd(d + 1, sum.y);
+                            if (D + 2 < lim) atomicAdd(d + 2, sum.z);
+                            if (D + 3 < lim) atomicAdd(d + 3, sum.w);
+                        }
                     }
                 }
             };
