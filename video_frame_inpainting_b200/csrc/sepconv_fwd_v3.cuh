@@ -175,9 +175,10 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                     constexpr int NK = (PITCH + 31) / 32;
                     // rows per batch and warp.  Single stream: ALL of a warp's rows in one batch (the H registers are not
                     // live yet, so 45 staging registers are free): one memory round trip per tile instead of four
-                    // (0.406 -> 0.393 ms at B = 160).  The dual-stream kernel keeps 4-row batches: with the first
-                    // stream's results live the large batch costs more than it hides (0.790 -> 0.867 ms, measured).
-                    constexpr int RB = DUAL ? 4 : TAI_HALO_RB;
+                    // (0.406 -> 0.393 ms at B = 160).  The dual-stream kernel takes two batches of 8 rows: with the first
+                    // stream's results live, one batch of 15 costs more than it hides (0.764 -> 0.836 ms, measured),
+                    // 4-row batches (four round trips) are 1.3 % behind (0.764 vs 0.754 ms).
+                    constexpr int RB = DUAL ? 8 : TAI_HALO_RB;
                     for (int c = 0; c < CG; ++c) {
                         const float *src = PAD ? in + ((long)(b * p.C + c0 + c)) * plane
                                                : in + ((long)(b * p.C + c0 + c)) * Hi * Wi;
