@@ -296,6 +296,19 @@ def test_slomo_training_environment_step(cuda):
     flow = env.gen_output['F_0_1'].detach()
     ref = GDL()(flow, torch.zeros_like(flow)).item()
     assert abs(env._smoothness(flow).item() - ref) <= 1e-5 * abs(ref)
+    # the warping loss read from the stage kernel's output equals the one that warps again, value and gradient
+    res = {}
+    for reuse in (True, False):
+        env.reuse_warps = reuse
+        env.generator.zero_grad()
+        env.forward_train()
+        env.compute_loss_G()
+        env.warping_loss.backward()
+        res[reuse] = (env.warping_loss.item(), [p.grad.detach().clone() for p in env.generator.parameters() if p.grad is not None])
+    assert res[True][0] == res[False][0]
+    assert len(res[True][1]) == len(res[False][1]) > 0
+    for a, b in zip(res[True][1], res[False][1]):
+        assert O.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
 
 
 def test_training_environment_matches_reference_step_golden(cuda):

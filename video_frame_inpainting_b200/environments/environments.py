@@ -382,6 +382,7 @@ class SloMoTrainingEnvironment(BaseTrainingEnvironment):
         for param in self.vgg16_conv.parameters():
             param.requires_grad = False
         self.warper = FlowWarper()
+        self.reuse_warps = True   # warping loss: take the per-t warped frames from the generator's stage kernel
         self.lambda_r, self.lambda_p, self.lambda_w, self.lambda_s = lambda_r, lambda_p, lambda_w, lambda_s
         self.lr_decay_count, self.lr_decay_rate, self.lr = lr_decay_count, lr_decay_rate, lr
 
@@ -403,8 +404,18 @@ class SloMoTrainingEnvironment(BaseTrainingEnvironment):
         as_rgb = lambda v: (v.expand(B, T, 3, H, W) if c_dim == 1 else v).reshape(B * T, 3, H, W)
         self.perceptual_loss = self.MSE_loss(self.vgg16_conv(as_rgb(pred)), self.vgg16_conv(as_rgb(gt)).detach())
         # warping loss (environments.py:584-586)
-        per_t = [self.l1_loss(self.warper(I0, out['F_t_0_collector'][:, i].contiguous()), gt[:, i])
-                 + self.l1_loss(self.warper(I1, out['F_t_1_collector'][:, i].contiguous()), gt[:, i]) for i in range(T)]
+        slomo = getattr(getattr(self.generator, 'module', self.generator), 'generator', None)
+        X = getattr(slomo, 'last_interp_input', None) if self.reuse_warps else None
+        if X is not None and X.shape[0] == T * B and X.shape[1] == 4 * c_dim + 4:
+            # g(I0, F_t_0) and g(I1, F_t_1) were formed by the time-batched stage kernel as channels [C, 2C) and
+            # [2C+4, 3C+4) of the refinement input (sample t*B + b); collector index i is time step T-1-i.  Same
+            # values bit for bit as warping again; the gradient reaches the flows through that kernel's adjoint.
+            blk = lambda i: X[(T - 1 - i) * B:(T - i) * B]
+            per_t = [self.l1_loss(blk(i)[:, c_dim:2 * c_dim], gt[:, i])
+                     + self.l1_loss(blk(i)[:, 2 * c_dim + 4:3 * c_dim + 4], gt[:, i]) for i in range(T)]
+        else:
+            per_t = [self.l1_loss(self.warper(I0, out['F_t_0_collector'][:, i].contiguous()), gt[:, i])
+                     + self.l1_loss(self.warper(I1, out['F_t_1_collector'][:, i].contiguous()), gt[:, i]) for i in range(T)]
         self.warping_loss = (self.l1_loss(self.warper(I0, F_1_0), I1) + self.l1_loss(self.warper(I1, F_0_1), I0)
                              + sum(per_t) / len(per_t))
         self.smooth_loss = self._smoothness(F_1_0) + self._smoothness(F_0_1)

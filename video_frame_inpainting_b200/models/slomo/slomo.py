@@ -162,11 +162,15 @@ class SloMo(nn.Module):
             # one pass over the T*B samples (sample n = t*B + b); collectors and pred come out in the reference's
             # reversed time order (slomo.py:332-340)
             interp_input, F_t_0_collector, F_t_1_collector = ops.SlomoInterpInputFunction.apply(I0, I1, F_0_1, F_1_0, T)
+            # the warped frames g(I0, F_t_0), g(I1, F_t_1) of every t are channels of this tensor: the training
+            # environment's warping loss reads them here instead of warping again (environments.py:584-586)
+            self.last_interp_input = interp_input if self.training else None
             delta_F_t_0, delta_F_t_1, V_t_0 = self.refine_dec(*self.refine_enc(interp_input))
             pred = ops.SlomoRefineBlendFunction.apply(I0, I1, F_t_0_collector, F_t_1_collector,
                                                       delta_F_t_0.contiguous(), delta_F_t_1.contiguous(),
                                                       V_t_0.contiguous(), T)
             return pred, F_0_1, F_1_0, F_t_0_collector, F_t_1_collector
+        self.last_interp_input = None
         preds, ft0s, ft1s = [], [], []
         for t_ in range(T):
             t = (t_ + 1) / (T + 1)
