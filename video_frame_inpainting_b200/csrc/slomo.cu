@@ -186,7 +186,32 @@ slomo_interp_input_bwd_kernel(const float *__restrict__ i0, const float *__restr
         const float b_u = ld_stream(f10 + fu), b_v = ld_stream(f10 + fv);
         const long base = (long)b * C * hw;
         float gau = 0.f, gav = 0.f, gbu = 0.f, gbv = 0.f;
+        // streamed operands of one time step: the gradients of X's warped-frame and flow channels and of the collectors
+        struct StepIn {
+            float go0[CT ? CT : 1], go1[CT ? CT : 1], xf[4], cf[4];
+        };
+        auto load_step = [&](int t, StepIn &in) {
+            const float *gxo = gX + ((long)t * B + b) * XC * hw + pix;
+            if (CT) {
+                TAI_CH_LOOP(CT, C) {
+                    in.go0[ch] = ld_stream(gxo + (long)(C + ch) * hw);
+                    in.go1[ch] = ld_stream(gxo + (long)(2 * C + 4 + ch) * hw);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) in.xf[k] = ld_stream(gxo + (long)(2 * C + k) * hw);
+            const long fo = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;
+            in.cf[0] = gft0c ? ld_stream(gft0c + fo) : 0.f;
+            in.cf[1] = gft0c ? ld_stream(gft0c + fo + hw) : 0.f;
+            in.cf[2] = gft1c ? ld_stream(gft1c + fo) : 0.f;
+            in.cf[3] = gft1c ? ld_stream(gft1c + fo + hw) : 0.f;
+        };
+        StepIn cur;
+        load_step(0, cur);
         for (int t = 0; t < T; ++t) {
+            StepIn nxt = cur;
+            if (t + 1 < T) load_step(t + 1, nxt);   // in flight under this step's gathers (the kernel was latency-bound:
+                                                    // three dependent round trips per pixel, issue slots 33 % busy)
             const TFlows f = combine_flows(tm, t, a_u, a_v, b_u, b_v);
             const WarpCoord c0 = warp_coord(x, y, f.t0u, f.t0v, g), c1 = warp_coord(x, y, f.t1u, f.t1v, g);
             const Taps w0 = make_taps(c0, H, W), w1 = make_taps(c1, H, W);
@@ -194,7 +219,8 @@ slomo_interp_input_bwd_kernel(const float *__restrict__ i0, const float *__restr
             const float *gxo = gX + ((long)t * B + b) * XC * hw + pix;
             float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f;
             TAI_CH_LOOP(CT, C) {
-                const float go0 = ld_stream(gxo + (long)(C + ch) * hw), go1 = ld_stream(gxo + (long)(2 * C + 4 + ch) * hw);
+                const float go0 = CT ? cur.go0[CT ? ch : 0] : ld_stream(gxo + (long)(C + ch) * hw);
+                const float go1 = CT ? cur.go1[CT ? ch : 0] : ld_stream(gxo + (long)(2 * C + 4 + ch) * hw);
                 const TapVals s0 = sample_with_derivative(i0 + base + (long)ch * hw, w0, W, q0.ax, q0.bx, q0.ay, q0.by);
                 const TapVals s1 = sample_with_derivative(i1 + base + (long)ch * hw, w1, W, q1.ax, q1.bx, q1.ay, q1.by);
                 gx0 += go0 * s0.ddx;
@@ -202,24 +228,16 @@ slomo_interp_input_bwd_kernel(const float *__restrict__ i0, const float *__restr
                 gx1 += go1 * s1.ddx;
                 gy1 += go1 * s1.ddy;
             }
-            float g0u = gx0 * sx + ld_stream(gxo + (long)(2 * C) * hw);
-            float g0v = gy0 * sy + ld_stream(gxo + (long)(2 * C + 1) * hw);
-            float g1u = gx1 * sx + ld_stream(gxo + (long)(2 * C + 2) * hw);
-            float g1v = gy1 * sy + ld_stream(gxo + (long)(2 * C + 3) * hw);
-            const long fo = ((long)b * T + (T - 1 - t)) * 2 * hw + pix;
-            if (gft0c) {
-                g0u += ld_stream(gft0c + fo);
-                g0v += ld_stream(gft0c + fo + hw);
-            }
-            if (gft1c) {
-                g1u += ld_stream(gft1c + fo);
-                g1v += ld_stream(gft1c + fo + hw);
-            }
+            const float g0u = gx0 * sx + cur.xf[0] + cur.cf[0];
+            const float g0v = gy0 * sy + cur.xf[1] + cur.cf[1];
+            const float g1u = gx1 * sx + cur.xf[2] + cur.cf[2];
+            const float g1v = gy1 * sy + cur.xf[3] + cur.cf[3];
             // F_t0 = c00 F01 + c01 F10 ; F_t1 = c10 F01 - c11 F10
             gau += tm.c00[t] * g0u + tm.c10[t] * g1u;
             gav += tm.c00[t] * g0v + tm.c10[t] * g1v;
             gbu += tm.c01[t] * g0u - tm.c11[t] * g1u;
             gbv += tm.c01[t] * g0v - tm.c11[t] * g1v;
+            cur = nxt;
         }
         gf01[fu] = gau;
         gf01[fv] = gav;
