@@ -208,20 +208,34 @@ sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
                 mbar_wait(&bars[0], parity);
                 LAB_T(1);
                 float h[FP][J];
-                {
+                // The H image is [row][tap][col]: rows 0 .. R0-1 cover the slab bytes of V chunk 0.  They are copied
+                // first, so that the first V chunk can be requested while the other rows are still being copied
+                // (its TMA latency used to be a serial phase of every tile: "wait for the first V chunk").
+                constexpr int R0 = (Cfg::CH_TAPS * Cfg::VROW + KS * 32 - 1) / (KS * 32);   // H rows overlapping V chunk 0
+                static_assert(R0 < FP, "the first V chunk must leave H rows to copy under its load");
 #pragma unroll
-                    for (int jj = 0; jj < J; ++jj)
+                for (int jj = 0; jj < J; ++jj)
 #pragma unroll
-                        for (int r = 0; r < FP; ++r)
-                            h[r][jj] = (ch + 4 * jj < KS) ? slab[(r * KS + 4 * jj) * 32 + swz[(r * KS + 4 * jj) & 7]] : 0.f;
+                    for (int r = 0; r < R0; ++r)
+                        h[r][jj] = (ch + 4 * jj < KS) ? slab[(r * KS + 4 * jj) * 32 + swz[(r * KS + 4 * jj) & 7]] : 0.f;
+                __syncthreads();  // the first R0 rows of H are in registers everywhere
+                if (threadIdx.x == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&bars[1], Cfg::CH_TAPS * Cfg::VROW * 4);
+                    tma_load_4d(slab, &maps.v[s], &bars[1], x0, y0, 0, b);
                 }
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj)
+#pragma unroll
+                    for (int r = R0; r < FP; ++r)
+                        h[r][jj] = (ch + 4 * jj < KS) ? slab[(r * KS + 4 * jj) * 32 + swz[(r * KS + 4 * jj) & 7]] : 0.f;
                 __syncthreads();  // H is in registers everywhere; the halo is complete
                 LAB_T(2);
-                // ---- V box -> slab in tap chunks; prefetch the next tile's boxes into L2 ----
+                // ---- the other V chunks; prefetch the next tile's boxes into L2 ----
                 if (threadIdx.x == 0) {
                     fence_proxy_async();
 #pragma unroll
-                    for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                    for (int q = 1; q < Cfg::NCHUNK; ++q) {
                         mbar_expect_tx(&bars[1 + q], Cfg::CH_TAPS * Cfg::VROW * 4);
                         tma_load_4d(slab + q * Cfg::CH_TAPS * Cfg::VROW, &maps.v[s], &bars[1 + q], x0, y0,
                                     q * Cfg::CH_TAPS, b);
