@@ -1,4 +1,5 @@
-# lab: the forward kernel with phases switched off one at a time (same scheme as vh_ablate_run.sh; timing only).
+# lab: the forward kernel with phases switched off one at a time (same scheme as vh_ablate_run.sh; timing only;
+# tools/lab/fw_ablate.patch for the v3 kernel, v5_ablate.patch (-DTAI_V5_ABLATE) for the v5 kernel).
 # Masks: 1 halo staging, 2 H TMA + wait, 4 V TMA + waits, 8 H slab -> registers, 16 all but one steady row per chunk.
 L=video_frame_inpainting_b200/lib/libtai_b200.so
 cp $L /tmp/orig.so

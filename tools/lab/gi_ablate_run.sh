@@ -1,4 +1,5 @@
-# lab: the gI kernel with phases switched off one at a time (same scheme as vh_ablate_run.sh; timing only).
+# lab: the gI kernel with phases switched off one at a time (same scheme as vh_ablate_run.sh; timing only;
+# tools/lab/gi_ablate.patch holds the masks 1, 2, 4 against the quad flush).
 # Masks: 1 flush body (merge + red.global), 2 flush barrier, 4 plain stores instead of atomics, 8 cross-lane reduction
 # and staging (FMAs kept alive), 16 all but one steady row per chunk, 32 H slab -> registers without LDS.
 L=video_frame_inpainting_b200/lib/libtai_b200.so
