@@ -54,7 +54,7 @@ static void run_variant(const char *name, FwdParams p, float *d_out, const std::
     constexpr int KS = LAB_KS, CG = LAB_CG;
     using Cfg = FwdV3Cfg<KS>;
     FwdV3Maps maps;
-    if (!make_kernel_map_tmap(&maps.h[0], p.hor[0], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, KS) ||
+    if (!make_kernel_map_tmap_swz(&maps.h[0], p.hor[0], p.B, KS, p.Ho, p.Wo, Cfg::TILE_H, KS) ||   // swizzled [row][tap][col] H box
         !make_kernel_map_tmap(&maps.v[0], p.ver[0], p.B, KS, p.Ho, p.Wo, Cfg::TILE_W, Cfg::TILE_H, Cfg::CH_TAPS)) { printf("tensor map failed\n"); return; }
     maps.h[1] = maps.h[0]; maps.v[1] = maps.v[0];
     p.ntx = ceil_div(p.Wo, Cfg::TILE_W);
