@@ -12,7 +12,7 @@ for (B, C, S) in [(16, 1, 128), (64, 1, 256), (64, 1, 512), (64, 3, 256), (16, 3
     for it in range(12):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ops.sepconv_forward(I, V, H); e1.record(); e1.synchronize()
+        e0.record(); ops.sepconv_forward(I, V, H, ks); e1.record(); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[1] * 1e-3
     by = 4.0 * (I.numel() + V.numel() + H.numel() + B * C * S * S)
