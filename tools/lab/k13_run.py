@@ -16,4 +16,14 @@ for (B, C, S) in [(16, 1, 128), (64, 1, 256), (64, 1, 512), (64, 3, 256), (16, 3
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[1] * 1e-3
     by = 4.0 * (I.numel() + V.numel() + H.numel() + B * C * S * S)
-    print(json.dumps({"shape": [B, C, S, S, ks], "us": round(t * 1e6, 1), "GBs": round(by / t / 1e9), "frac_hbm": round(by / t / 6553e9, 3)}))
+    gO = torch.rand(B, C, S, S, device=dev)
+    tb = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.sepconv_backward(gO, I, V, H, ks, (True, True, True)); e1.record(); e1.synchronize()
+        tb.append(e0.elapsed_time(e1))
+    tb = sorted(tb)[1] * 1e-3
+    byb = 4.0 * (2 * I.numel() + 4 * V.numel() + 2 * gO.numel())
+    print(json.dumps({"shape": [B, C, S, S, ks], "fwd_us": round(t * 1e6, 1), "fwd_frac_hbm": round(by / t / 6553e9, 3),
+                      "bwd_us": round(tb * 1e6, 1), "bwd_frac_hbm": round(byb / tb / 6553e9, 3)}))
