@@ -5,7 +5,7 @@ from video_frame_inpainting_b200 import ops
 dev = torch.device("cuda:0")
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 for (B, C, S) in [(16, 1, 128), (64, 1, 256), (64, 1, 512), (64, 3, 256), (16, 3, 512)]:
-    ks = 13
+    ks = int(os.environ.get("KS", "13"))
     I = torch.rand(B, C, S + ks - 1, S + ks - 1, device=dev)
     V, H = torch.rand(B, ks, S, S, device=dev), torch.rand(B, ks, S, S, device=dev)
     ts = []

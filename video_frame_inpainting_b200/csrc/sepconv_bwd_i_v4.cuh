@@ -145,8 +145,9 @@ __device__ __forceinline__ void gi_row_v4(const float *__restrict__ vrow,
 }
 
 template <int KS, bool FOLD>
-// ks <= 16: few taps in registers (80 registers), six CTAs per SM put more boxes in flight (ks = 13 backward: + 10 %)
-__global__ void __launch_bounds__(128, (KS <= 16 ? 6 : 3))
+// small windows keep few taps in registers: six CTAs per SM for ks <= 16 (80 registers; ks = 13 backward + 10 %), four for
+// ks <= 28 (ks = 25: + 4 %) put more boxes in flight where the op is HBM-bound
+__global__ void __launch_bounds__(128, (KS <= 16 ? 6 : KS <= 28 ? 4 : 3))
 sepconv_bwd_i_v4_kernel(const __grid_constant__ GiV4Maps maps, const BwdParams p)
 {
     using Cfg = GiV4Cfg<KS>;

@@ -106,8 +106,9 @@ __device__ __forceinline__ void vh_row_v3(const float *__restrict__ srow, const 
 }
 
 template <int KS, int CG, bool PAD>
-// ks <= 16: few taps in registers (80 registers), six CTAs per SM put more boxes in flight (ks = 13 backward: + 10 %)
-__global__ void __launch_bounds__(128, (KS <= 16 ? 6 : 3))
+// small windows keep few taps in registers: six CTAs per SM for ks <= 16 (80 registers; ks = 13 backward + 10 %), four for
+// ks <= 28 (ks = 25: + 4 %) put more boxes in flight where the op is HBM-bound
+__global__ void __launch_bounds__(128, (KS <= 16 ? 6 : KS <= 28 ? 4 : 3))
 sepconv_bwd_vh_v3_kernel(const __grid_constant__ VhV3Maps maps, const BwdParams p)
 {
     static_assert(BP == 4, "the reduce-scatter assumes 4 output rows == 4 tap groups");

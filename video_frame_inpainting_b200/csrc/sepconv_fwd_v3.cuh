@@ -101,7 +101,7 @@ __device__ __forceinline__ void fwd_row_v3(const float *__restrict__ srow, const
 template <int KS, int CG, bool PAD, bool DUAL>
 // small windows (ks <= 16) are HBM-bound and keep few taps in registers: six CTAs per SM put more boxes in flight
 // (ks = 13, C = 1, [64,1,512,512]: 65.5 -> 68.9 % of the measured copy bandwidth; at C = 3 four CTAs were no gain)
-__global__ void __launch_bounds__(128, (CG == 1 ? (KS <= 16 ? 6 : TAI_FWD_MIN_CTAS) : 2))
+__global__ void __launch_bounds__(128, (CG == 1 ? (KS <= 16 ? 6 : KS <= 28 ? 4 : TAI_FWD_MIN_CTAS) : 2))
 sepconv_fwd_v3_kernel(const __grid_constant__ FwdV3Maps maps, const FwdParams p)
 {
     using Cfg = FwdV3Cfg<KS>;
